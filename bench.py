@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""bench.py -- training views/sec of the rasterizer hot path (BASELINE.json metric) on N GPUs of one node.
+
+  python bench.py --gpus 1 --steps 20 --warmup 5                       # our sm_100a path
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+         bench.py --gpus N --steps K --warmup W                         # view-parallel, one rank per GPU
+  python bench.py --impl reference ...                                  # the reference's own CUDA kernels (oracle/_ref)
+
+A "step" is one training view per rank through the public API: gaussian_renderer.render() (activations, SH
+concatenation, rasterizer forward) -> L1 image loss -> backward to the six raw parameter leaves; for N > 1 the
+per-Gaussian gradients are then summed across ranks with ONE NCCL all-reduce (the path's only exchange).
+Workload = BASELINE.json configs[2]: 3M synthetic Gaussians, SH degree 3, 1920x1080, synthetic cameras.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "training views/sec at 3M Gaussians 1080p"
+UNIT = "views/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--P", type=int, default=3_000_000, help="number of Gaussians (default: the 3M workload)")
+    ap.add_argument("--width", type=int, default=1920)
+    ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--cams", type=int, default=16, help="distinct synthetic cameras cycled through")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks (B200_PROFILING.md recipe), sampled DURING the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "index,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference's kernels behind the same autograd surface (only for --impl reference)
+# ------------------------------------------------------------------------------------------------
+def make_reference_render():
+    """render() whose rasterizer is the reference's own CUDA code (oracle/_ref/libref_rasterizer.so: forward.cu,
+    backward.cu, rasterizer_impl.cu compiled unmodified).  Allocation behaviour follows the reference's torch binding
+    (zero-filled outputs, RAST/rasterize_points.cu:79-80,254-262)."""
+    import ctypes as C
+    path = os.path.join(ROOT, "oracle", "_ref", "libref_rasterizer.so")
+    if not os.path.exists(path):
+        return None
+    lib = C.CDLL(path)
+    vp, i, f = C.c_void_p, C.c_int, C.c_float
+    lib.ref_state_create.restype = vp
+    lib.ref_forward.restype = i
+    lib.ref_forward.argtypes = [vp, i, i, i, i, vp, i, i, vp, vp, vp, vp, vp, f, vp, vp, vp, vp, vp, f, f, i, vp, vp, vp, vp]
+    lib.ref_backward.restype = None
+    lib.ref_backward.argtypes = [vp, i, i, i, vp, i, i, vp, vp, vp, vp, f, vp, vp, vp, vp, vp, f, f, vp, vp] + [vp] * 9
+    state = lib.ref_state_create()
+
+    class RefRasterize(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, means3D, means2D, sh, opacities, scales, rotations, cam, bg, tanx, tany, H, W, deg):
+            P, M = means3D.shape[0], sh.shape[1]
+            color = torch.full((3, H, W), 0.0, dtype=torch.float32, device=means3D.device)
+            radii = torch.full((P,), 0, dtype=torch.int32, device=means3D.device)
+            ms, shc, op, sc, ro = means3D.contiguous(), sh.contiguous(), opacities.contiguous(), scales.contiguous(), rotations.contiguous()
+            lib.ref_forward(state, 0, P, deg, M, bg.data_ptr(), W, H, ms.data_ptr(), shc.data_ptr(), None, op.data_ptr(), sc.data_ptr(),
+                            1.0, ro.data_ptr(), None, cam.world_view_transform.data_ptr(), cam.full_proj_transform.data_ptr(),
+                            cam.camera_center.data_ptr(), tanx, tany, 0, color.data_ptr(), radii.data_ptr(), None, None)
+            ctx.save_for_backward(ms, shc, sc, ro, radii, bg)
+            ctx.cam, ctx.meta = cam, (tanx, tany, H, W, deg)
+            return color, radii
+
+        @staticmethod
+        def backward(ctx, g_color, _):
+            ms, shc, sc, ro, radii, bg = ctx.saved_tensors
+            tanx, tany, H, W, deg = ctx.meta
+            cam = ctx.cam
+            P, M = ms.shape[0], shc.shape[1]
+            z = lambda *s: torch.zeros(s, dtype=torch.float32, device=ms.device)  # noqa: E731
+            d2, dcon, dop, dcol, d3, dcov, dsh, dsc, dro = z(P, 3), z(P, 2, 2), z(P, 1), z(P, 3), z(P, 3), z(P, 6), z(P, M, 3), z(P, 3), z(P, 4)
+            g = g_color.contiguous()
+            lib.ref_backward(state, P, deg, M, bg.data_ptr(), W, H, ms.data_ptr(), shc.data_ptr(), None, sc.data_ptr(), 1.0, ro.data_ptr(),
+                             None, cam.world_view_transform.data_ptr(), cam.full_proj_transform.data_ptr(), cam.camera_center.data_ptr(),
+                             tanx, tany, radii.data_ptr(), g.data_ptr(), d2.data_ptr(), dcon.data_ptr(), dop.data_ptr(), dcol.data_ptr(),
+                             d3.data_ptr(), dcov.data_ptr(), dsh.data_ptr(), dsc.data_ptr(), dro.data_ptr())
+            return d3, d2, dsh, dop, dsc, dro, None, None, None, None, None, None, None
+
+    def render(cam, pc, pipe, bg):
+        xyz = pc.get_xyz
+        ssp = torch.zeros_like(xyz, requires_grad=True) + 0
+        img, radii = RefRasterize.apply(xyz, ssp, pc.get_features, pc.get_opacity, pc.get_scaling, pc.get_rotation, cam, bg,
+                                        math.tan(cam.FoVx * 0.5), math.tan(cam.FoVy * 0.5), int(cam.image_height),
+                                        int(cam.image_width), pc.active_sh_degree)
+        return {"render": img, "viewspace_points": ssp, "visibility_filter": radii > 0, "radii": radii}
+    return render
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_oracle_sample(scene, cam, W, H):
+    """the CPU port (oracle/lgo.c, single thread) on ONE view of the same workload: forward + backward."""
+    from oracle.lgo import Oracle, View
+    act = scene["act"]
+    v = View(W, H, cam.tanfovx, cam.tanfovy, cam.world_view_transform, cam.full_proj_transform, cam.camera_center,
+             np.zeros(3, np.float32), 3, 1.0)
+    o = Oracle()
+    rng = np.random.default_rng(0)
+    dpix = rng.standard_normal((3, H, W)).astype(np.float32)
+    t0 = time.perf_counter()
+    f = o.forward(v, act["means3D"], act["opacities"], shs=act["shs"], scales=act["scales"], rotations=act["rotations"])
+    o.backward(v, f, dpix, act["means3D"], shs=act["shs"], scales=act["scales"], rotations=act["rotations"])
+    dt = time.perf_counter() - t0
+    return 1.0 / dt, dt
+
+
+def main():
+    args = parse_args()
+    from lightgaussian_b200 import parallel
+    rank, world, local = parallel.init_from_env()
+    if args.impl == "reference" and rank != 0:
+        return 0  # the reference is single-GPU: rank 0 alone runs it
+    if args.impl == "reference":
+        world = 1
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU path in the product)"
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+
+    from lightgaussian_b200.model import GaussianParams, TorchCamera, pipeline_params
+    from lightgaussian_b200.synth import make_scene, make_cameras
+    from lightgaussian_b200.trainstep import train_view
+    P, W, H = args.P, args.width, args.height
+    scene = make_scene(P, sh_degree=3, seed=0)
+    cams_np = make_cameras(args.cams, W, H)
+    pc = GaussianParams(scene["raw"], 3, dev)
+    cams = [TorchCamera(c, dev) for c in cams_np]
+    bg = torch.zeros(3, device=dev)
+    pipe = pipeline_params()
+    flat = parallel.FlatGrads(pc.parameters())
+
+    gen = torch.Generator().manual_seed(1234)
+    targets_host = [torch.rand(3, H, W, generator=gen).pin_memory() for _ in range(min(args.cams, 8))]
+    targets_dev = [t.to(dev) for t in targets_host]
+    cam_host = [(torch.from_numpy(c.world_view_transform).pin_memory(), torch.from_numpy(c.full_proj_transform).pin_memory(),
+                 torch.from_numpy(c.camera_center).pin_memory()) for c in cams_np]
+
+    if args.impl == "ours":
+        from lightgaussian_b200 import capi, rasterizer
+        from lightgaussian_b200.renderer import render as render_fn
+        capi.load()
+        kind = None
+    else:
+        render_fn = make_reference_render()
+        kind = "reference"
+        if render_fn is None:
+            kind = "port"
+
+    def view_index(step):
+        return (step * world + rank) % len(cams)
+
+    def step_resident(step):
+        i = view_index(step)
+        flat.zero()
+        loss = train_view(render_fn, cams[i], pc, pipe, bg, targets_dev[i % len(targets_dev)])
+        flat.allreduce(world)
+        return loss
+
+    def step_e2e(step):
+        i = view_index(step)
+        cam = cams[i]
+        wv, fp, cc = cam_host[i]
+        cam.world_view_transform.copy_(wv, non_blocking=True)      # H2D: this step's camera
+        cam.full_proj_transform.copy_(fp, non_blocking=True)
+        cam.camera_center.copy_(cc, non_blocking=True)
+        tgt = targets_host[i % len(targets_host)].to(dev, non_blocking=True)  # H2D: this step's target image
+        flat.zero()
+        loss = train_view(render_fn, cam, pc, pipe, bg, tgt)
+        flat.allreduce(world)
+        return float(loss.item())                                   # D2H: the step's result
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+
+    def timed(fn, steps, sampler=None):
+        barrier()
+        torch.cuda.synchronize()
+        if sampler:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for s in range(steps):
+            fn(args.warmup + s)
+        e1.record()
+        torch.cuda.synchronize()
+        clocks = sampler.stop() if sampler else None
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+        return float(ms.item()), clocks
+
+    # ---------------- the reference arm when its kernels could not be built: CPU port ----------------
+    if args.impl == "reference" and kind == "port":
+        v, dt = cpu_oracle_sample(scene, cams_np[0], W, H)
+        line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": 1, "steps": 1, "warmup": 0,
+                "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": {"workload": f"{P} Gaussians SH3 {W}x{H} fwd+bwd, 1 view (CPU port of the reference algorithm)"},
+                "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": "1 view forward+backward, oracle/lgo.c single thread"},
+                "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    # ---------------- warm-up, then the timed regions ----------------
+    for s in range(args.warmup):
+        step_resident(s)
+    torch.cuda.synchronize()
+    n0 = capi.launch_count() if args.impl == "ours" else 0
+    ms, clocks = timed(step_resident, args.steps, ClockSampler(local) if rank == 0 else None)
+    launches = (capi.launch_count() - n0) if args.impl == "ours" else 0
+    views = args.steps * world
+    value = views / (ms * 1e-3)
+
+    e2e = None
+    if not args.no_e2e:
+        for s in range(2):
+            step_e2e(s)
+        ms_e, _ = timed(step_e2e, args.steps)
+        h2d = 3 * H * W * 4 + (16 + 16 + 3) * 4
+        e2e = {"value": views / (ms_e * 1e-3), "unit": UNIT, "ms_per_step": ms_e / args.steps, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": 4}
+
+    # ---------------- roofline of the dominant kernel (rank 0, our arm) ----------------
+    roofline, stages = None, None
+    if args.impl == "ours" and not args.no_roofline and rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        capi.profile_collect()
+        capi.profile_enable(True)
+        nprof = min(args.steps, 10)
+        vis, Rs = [], []
+        for s in range(nprof):
+            i = view_index(args.warmup + s)
+            flat.zero()
+            pkg = render_fn(cams[i], pc, pipe, bg)
+            (pkg["render"] - targets_dev[i % len(targets_dev)]).abs().mean().backward()
+            vis.append(int((pkg["radii"] > 0).sum().item()))
+            Rs.append(int(rasterizer.last_num_rendered()))
+        prof = capi.profile_collect()
+        capi.profile_enable(False)
+        Pv, R, N, M = float(np.mean(vis)), float(np.mean(Rs)), W * H, 16
+        # ALGORITHMIC bytes per launch (split per kernel in DESIGN.md section 4)
+        alg = {
+            "preprocess_kernel": 12 * P + Pv * (32 + 12 * M) + 4 * P + 40 * Pv,
+            "depth_sort(cub)": 16 * P, "scan(cub)": 8 * P, "emit_kernel": 12 * Pv + 6 * R, "tile_sort(cub)": 12 * R,
+            "ranges_kernel": 2 * R,
+            "blend_forward_kernel": 40 * R + 20 * N,
+            "blend_backward_kernel": 20 * N + 40 * R + 44 * Pv,
+            "preprocess_backward_kernel": 44 * Pv + 12 * P + Pv * (32 + 12 * M) + P * (56 + 12 * M),
+            "memset": 48 * P,
+        }
+        stages = {k: {"ms_per_launch": ms_k / n, "launches": n, "alg_bytes": alg.get(k),
+                      "gbs": (alg[k] / (ms_k / n * 1e-3) / 1e9) if k in alg else None}
+                  for k, (ms_k, n) in prof.items() if n > 0}
+        top = max(stages, key=lambda k: stages[k]["ms_per_launch"] * stages[k]["launches"])
+        ach = stages[top]["gbs"]
+        tot_ms = sum(v["ms_per_launch"] * v["launches"] for v in stages.values()) / nprof
+        Bf = 12 * P + Pv * (32 + 12 * M) + 4 * P + 40 * Pv + 28 * R + 40 * R + 20 * N
+        Bb = 20 * N + 40 * R + 88 * Pv + 12 * P + Pv * (32 + 12 * M) + P * (56 + 12 * M)
+        roofline = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "traffic": None, "peak_source": peak_src,
+                    "share_of_native_time": stages[top]["ms_per_launch"] * stages[top]["launches"] / nprof / tot_ms,
+                    "whole_view": {"alg_bytes": Bf + Bb, "native_ms_per_view": tot_ms,
+                                   "achieved": (Bf + Bb) / (tot_ms * 1e-3) / 1e9, "frac": (Bf + Bb) / (tot_ms * 1e-3) / 1e9 / peak},
+                    "measured": {"P_visible": Pv, "num_rendered": R}}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        if args.impl == "ours":
+            v_cpu, dt = cpu_oracle_sample(scene, cams_np[0], W, H)
+            cpu_baseline = {"value": v_cpu, "unit": UNIT, "cores": 1, "kind": "port",
+                            "sample": f"1 view forward+backward of the same workload ({dt:.1f} s), oracle/lgo.c single thread; host has {os.cpu_count()} cores"}
+        else:
+            cpu_baseline = {"value": value, "unit": UNIT, "cores": 0, "kind": "reference",
+                            "sample": "the reference has NO CPU implementation of this path: this arm times its own CUDA kernels "
+                                      "(oracle/_ref: forward.cu/backward.cu/rasterizer_impl.cu compiled unmodified for sm_100a) on the same GPU, "
+                                      f"same steps; host has {os.cpu_count()} cores"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": f"{P} Gaussians SH degree 3, {W}x{H}, {len(cams)} synthetic cameras (Fibonacci sphere r=3), "
+                                   "step = render()+L1+backward to raw leaves" + (" + 1 NCCL all-reduce of gradients" if world > 1 else ""),
+                       "gaussians": P, "resolution": [W, H], "views_per_step": world, "parallelism": f"view-parallel x{world}",
+                       "l2_policy": "inputs larger than L2 (>=0.7 GB of parameters streamed per step)",
+                       "grad_allreduce_bytes": flat.nbytes if world > 1 else 0},
+            "clocks": clocks, "gpu_launches": launches,
+        }
+        if args.impl == "reference":
+            line["impl"] = "reference"
+            line["e2e"] = {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+            if e2e:
+                line["e2e_host_buffers"] = e2e
+        else:
+            line["e2e"] = e2e
+        if roofline:
+            line["roofline"] = roofline
+            line["stages"] = stages
+        if cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline
+        print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,133 @@
+/*
+ * lgrast.h -- C-ABI of liblgrast.so, the B200 (sm_100a) rasterizer for LightGaussian's hot path.
+ *
+ * Drop-in boundary.  The four work entry points replace, one for one, the static C++ API the
+ * reference's torch binding calls (RAST = submodules/compress-diff-gaussian-rasterization):
+ *
+ *   lgr_forward        <- CudaRasterizer::Rasterizer::forward       RAST/cuda_rasterizer/rasterizer.h:35-57
+ *   lgr_forward_count  <- CudaRasterizer::Rasterizer::forwardCount  RAST/cuda_rasterizer/rasterizer.h:60-84
+ *   lgr_backward       <- CudaRasterizer::Rasterizer::backward      RAST/cuda_rasterizer/rasterizer.h:86-112
+ *   lgr_mark_visible   <- CudaRasterizer::Rasterizer::markVisible   RAST/cuda_rasterizer/rasterizer.h:28-33
+ *
+ * Conventions kept from the reference: every data pointer is a DEVICE pointer to contiguous float32 /
+ * int32 memory owned by the caller; a NULL pointer means "input absent" (shs / colors_precomp /
+ * scales / rotations / cov3D_precomp); viewmatrix and projmatrix are the TRANSPOSED 4x4 matrices
+ * (scene/cameras.py:70-84); out_color is planar [3,H,W]; the three opaque state blobs are obtained
+ * through caller-supplied allocators in the order geometry -> image -> binning (the last one only
+ * after the instance count is known) and are handed back unchanged to lgr_backward.
+ *
+ * Differences (all additive): plain function-pointer allocators instead of std::function, an explicit
+ * cudaStream_t (the reference launches on the legacy default stream), an int status return with
+ * lgr_last_error(), and gradient outputs that need NOT be zero-initialised by the caller.
+ *
+ * No torch / C++ types cross this boundary.
+ */
+#ifndef LGRAST_H_INCLUDED
+#define LGRAST_H_INCLUDED
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LGR_ABI_VERSION 1
+
+/* status codes */
+#define LGR_OK 0
+#define LGR_ERR_INVALID_ARG 1 /* bad sizes / required pointer missing */
+#define LGR_ERR_CUDA 2        /* a CUDA runtime call or kernel failed; see lgr_last_error() */
+#define LGR_ERR_ALLOC 3       /* an allocator callback returned NULL */
+
+/* Replaces std::function<char*(size_t)> (RAST/cuda_rasterizer/rasterizer.h:36-38): must return a device
+ * pointer to at least `bytes` bytes, aligned to 256 B, that stays valid until the matching backward call. */
+typedef char* (*lgr_alloc_fn)(void* user, size_t bytes);
+
+/* Per-view constants: the numeric fields of GaussianRasterizationSettings
+ * (RAST/diff_gaussian_rasterization/__init__.py:248-261). */
+typedef struct lgr_view {
+    int32_t image_width;
+    int32_t image_height;
+    float tan_fovx;
+    float tan_fovy;
+    float scale_modifier;
+    int32_t sh_degree;       /* active degree D (0..3) */
+    int32_t prefiltered;     /* as the reference: a culled point traps the kernel when set */
+    int32_t debug;           /* synchronise and check after every stage */
+    const float* viewmatrix; /* device, 16 floats, transposed W2C */
+    const float* projmatrix; /* device, 16 floats, transposed Proj*W2C */
+    const float* campos;     /* device, 3 floats */
+    const float* background; /* device, 3 floats */
+} lgr_view;
+
+/* Forward render.  P Gaussians, M stored SH coefficients per channel (0 when shs == NULL).
+ * Writes out_color[3*H*W], radii[P]; *num_rendered receives the reference's instance count
+ * (sum over Gaussians of the tile-rectangle area, rasterizer_impl.cu:278-282). */
+int lgr_forward(const lgr_view* view, int P, int M,
+                const float* means3D, const float* shs, const float* colors_precomp, const float* opacities,
+                const float* scales, const float* rotations, const float* cov3D_precomp,
+                lgr_alloc_fn geometry_alloc, void* geometry_user,
+                lgr_alloc_fn binning_alloc, void* binning_user,
+                lgr_alloc_fn image_alloc, void* image_user,
+                float* out_color, int32_t* radii, int32_t* num_rendered, void* cuda_stream);
+
+/* Forward render + Global Significance accumulation (RAST/cuda_rasterizer/forward.cu:378-501).
+ * gaussians_count[P] and important_score[P] are fully written (no zero-init needed):
+ *   gaussians_count[i] = number of (pixel, i) pairs that were blended in this view (exact, deterministic),
+ *   important_score[i] = opacity[i] * gaussians_count[i]. */
+int lgr_forward_count(const lgr_view* view, int P, int M,
+                      const float* means3D, const float* shs, const float* colors_precomp, const float* opacities,
+                      const float* scales, const float* rotations, const float* cov3D_precomp,
+                      lgr_alloc_fn geometry_alloc, void* geometry_user,
+                      lgr_alloc_fn binning_alloc, void* binning_user,
+                      lgr_alloc_fn image_alloc, void* image_user,
+                      float* out_color, int32_t* gaussians_count, float* important_score, int32_t* radii,
+                      int32_t* num_rendered, void* cuda_stream);
+
+/* Backward.  The three blobs and num_rendered come from the matching lgr_forward call.
+ * Outputs (all fully written): dL_dmeans2D[P,3], dL_dcolors[P,3], dL_dopacity[P], dL_dmeans3D[P,3],
+ * dL_dcov3D[P,6], dL_dsh[P,M,3] (may be NULL when M == 0), dL_dscales[P,3], dL_drotations[P,4]
+ * -- the tuple RAST/rasterize_points.cu:298 returns. */
+int lgr_backward(const lgr_view* view, int P, int M, int num_rendered,
+                 const float* means3D, const float* shs, const float* colors_precomp,
+                 const float* scales, const float* rotations, const float* cov3D_precomp,
+                 const int32_t* radii, char* geometry_blob, char* binning_blob, char* image_blob,
+                 const float* dL_dout_color,
+                 float* dL_dmeans2D, float* dL_dcolors, float* dL_dopacity, float* dL_dmeans3D,
+                 float* dL_dcov3D, float* dL_dsh, float* dL_dscales, float* dL_drotations, void* cuda_stream);
+
+/* present[i] = (view-space z of point i) > 0.2   (RAST/cuda_rasterizer/rasterizer_impl.cu:54-66, auxiliary.h:139-164) */
+int lgr_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix, uint8_t* present,
+                     void* cuda_stream);
+
+/* ---- introspection (tests, diagnostics) ---- */
+int lgr_abi_version(void);
+const char* lgr_last_error(void); /* thread-local, valid until the next failing call on this thread */
+
+/* Byte offsets of the per-Gaussian arrays inside a geometry blob for P points, so tests can read the
+ * intermediates the way RAST/cuda_rasterizer/rasterizer_impl.cu:155-170 lays them out for the reference.
+ * out[0]=depth(f32) out[1]=means2D(float2) out[2]=conic_opacity(float4) out[3]=rgb(float4, w unused)
+ * out[4]=cov3D(6 f32) out[5]=clamped(u8 bitmask r=1,g=2,b=4) out[6]=tiles_touched(u32) out[7]=depth-sorted ids(u32)
+ * Returns the total geometry blob size. */
+size_t lgr_geometry_layout(int P, size_t* out, int n_out);
+/* out[0]=final_T(f32[N]) out[1]=n_contrib(u32[N]) out[2]=ranges(uint2[tiles]).  Returns image blob size. */
+size_t lgr_image_layout(int width, int height, size_t* out, int n_out);
+/* out[0]=point_list(u32[R]) -- per-tile, depth-sorted Gaussian ids.  Returns binning blob size for R instances. */
+size_t lgr_binning_layout(int num_rendered, int width, int height, size_t* out, int n_out);
+/* Kernel launches issued by this library since load (for bench.py's gpu_launches). */
+uint64_t lgr_launch_count(void);
+
+/* Optional per-stage device timing: when enabled every launch is bracketed by CUDA events on its stream.
+ * lgr_profile_collect() synchronises the device, writes the accumulated milliseconds and launch counts of each
+ * stage (index < lgr_profile_stage_count()) and resets them.  Timing mode adds event overhead; do not use it
+ * inside a throughput measurement. */
+int lgr_profile_enable(int on);
+int lgr_profile_stage_count(void);
+const char* lgr_profile_stage_name(int stage);
+int lgr_profile_collect(double* ms_out, uint64_t* launches_out, int n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LGRAST_H_INCLUDED */

@@ -1,0 +1,170 @@
+"""ctypes binding of the C-ABI in include/lgrast.h.  torch is used only for device memory
+(`tensor.data_ptr()`) and the current stream; no torch type crosses into liblgrast.so.
+
+There is deliberately NO fallback: if liblgrast.so is missing or fails to load, importing the
+rasterizer raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import torch
+
+from . import build as _build
+
+LGR_OK = 0
+
+
+class LgrView(C.Structure):
+    """struct lgr_view (include/lgrast.h)"""
+    _fields_ = [
+        ("image_width", C.c_int32), ("image_height", C.c_int32),
+        ("tan_fovx", C.c_float), ("tan_fovy", C.c_float), ("scale_modifier", C.c_float),
+        ("sh_degree", C.c_int32), ("prefiltered", C.c_int32), ("debug", C.c_int32),
+        ("viewmatrix", C.c_void_p), ("projmatrix", C.c_void_p), ("campos", C.c_void_p), ("background", C.c_void_p),
+    ]
+
+
+ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t)
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+def lib_path() -> str:
+    return _build.LIB_PATH
+
+
+def load():
+    """Load (building first if the sources are newer and nvcc is present) and type the library."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        path = _build.LIB_PATH
+        if not os.path.exists(path):
+            path = _build.build_library()
+        lib = C.CDLL(path)
+        if lib.lgr_abi_version() != 1:
+            raise RuntimeError("liblgrast.so ABI version mismatch")
+        vp, i32 = C.c_void_p, C.c_int
+        fwd_common = [C.POINTER(LgrView), i32, i32] + [vp] * 7 + [ALLOC_FN, vp, ALLOC_FN, vp, ALLOC_FN, vp]
+        lib.lgr_forward.restype = i32
+        lib.lgr_forward.argtypes = fwd_common + [vp, vp, C.POINTER(C.c_int32), vp]
+        lib.lgr_forward_count.restype = i32
+        lib.lgr_forward_count.argtypes = fwd_common + [vp, vp, vp, vp, C.POINTER(C.c_int32), vp]
+        lib.lgr_backward.restype = i32
+        lib.lgr_backward.argtypes = [C.POINTER(LgrView), i32, i32, i32] + [vp] * 20
+        lib.lgr_mark_visible.restype = i32
+        lib.lgr_mark_visible.argtypes = [i32, vp, vp, vp, vp, vp]
+        lib.lgr_last_error.restype = C.c_char_p
+        lib.lgr_launch_count.restype = C.c_uint64
+        for name in ("lgr_geometry_layout", "lgr_image_layout", "lgr_binning_layout"):
+            getattr(lib, name).restype = C.c_size_t
+        lib.lgr_geometry_layout.argtypes = [i32, C.POINTER(C.c_size_t), i32]
+        lib.lgr_image_layout.argtypes = [i32, i32, C.POINTER(C.c_size_t), i32]
+        lib.lgr_binning_layout.argtypes = [i32, i32, i32, C.POINTER(C.c_size_t), i32]
+        lib.lgr_profile_stage_name.restype = C.c_char_p
+        lib.lgr_profile_collect.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_uint64), i32]
+        _lib = lib
+    return _lib
+
+
+class LgrError(RuntimeError):
+    pass
+
+
+def check(status: int, what: str):
+    if status != LGR_OK:
+        msg = load().lgr_last_error()
+        raise LgrError(f"{what} failed (status {status}): {msg.decode() if msg else ''}")
+
+
+# ---- allocator callback -------------------------------------------------------------------------
+# One C callback for all calls; `user` is a small integer naming a slot that receives the tensor.
+_slots = {}
+_slot_lock = threading.Lock()
+_next_slot = [1]
+
+
+class BlobSlot:
+    """Receives one opaque state blob (a uint8 torch tensor) from the library's allocator callback."""
+
+    def __init__(self, device):
+        self.device = device
+        self.tensor = None
+        with _slot_lock:
+            self.key = _next_slot[0]
+            _next_slot[0] += 1
+            _slots[self.key] = self
+
+    def release(self):
+        with _slot_lock:
+            _slots.pop(self.key, None)
+
+
+def _alloc(user, nbytes):
+    slot = _slots.get(user)
+    if slot is None:
+        return None
+    try:
+        t = torch.empty(int(nbytes), dtype=torch.uint8, device=slot.device)
+    except Exception:  # out of memory -> NULL -> LGR_ERR_ALLOC
+        return None
+    slot.tensor = t
+    return t.data_ptr()
+
+
+ALLOC_CB = ALLOC_FN(_alloc)
+
+
+def ptr(t):
+    """Device pointer of a tensor, or NULL for None / empty tensors (the reference's 'input absent')."""
+    if t is None or t.numel() == 0:
+        return None
+    return t.data_ptr()
+
+
+def current_stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def launch_count() -> int:
+    return int(load().lgr_launch_count())
+
+
+def geometry_layout(P: int):
+    out = (C.c_size_t * 8)()
+    total = load().lgr_geometry_layout(P, out, 8)
+    names = ["depth", "means2D", "conic_opacity", "rgb", "cov3D", "clamped", "tiles_touched", "sorted_ids"]
+    return dict(zip(names, list(out))), int(total)
+
+
+def image_layout(W: int, H: int):
+    out = (C.c_size_t * 3)()
+    total = load().lgr_image_layout(W, H, out, 3)
+    return dict(zip(["final_T", "n_contrib", "ranges"], list(out))), int(total)
+
+
+def binning_layout(R: int, W: int, H: int):
+    out = (C.c_size_t * 1)()
+    total = load().lgr_binning_layout(R, W, H, out, 1)
+    return dict(point_list=int(out[0])), int(total)
+
+
+def profile_enable(on: bool):
+    load().lgr_profile_enable(int(on))
+
+
+def profile_collect():
+    """{stage name: (total ms, launches)} since the last collect; synchronises the device."""
+    lib = load()
+    n = lib.lgr_profile_stage_count()
+    ms = (C.c_double * n)()
+    cnt = (C.c_uint64 * n)()
+    check(lib.lgr_profile_collect(ms, cnt, n), "lgr_profile_collect")
+    return {lib.lgr_profile_stage_name(k).decode(): (float(ms[k]), int(cnt[k])) for k in range(n)}

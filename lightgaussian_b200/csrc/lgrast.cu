@@ -1,0 +1,1106 @@
+// lgrast.cu -- sm_100a kernels and the C-ABI (include/lgrast.h) of the B200 rasterizer.
+//
+// Pipeline per view (reference call order: RAST/cuda_rasterizer/rasterizer_impl.cu:198-337):
+//
+//   preprocess_kernel     per Gaussian: cull, EWA projection, SH->RGB, tile rectangle        (K1)
+//   depth sort            CUB radix sort of P 32-bit depth keys                               (replaces part of L2)
+//   scan                  CUB inclusive sum of tiles_touched in depth order                   (L1)
+//   emit_kernel           one (tile, id) instance per overlapped tile, in depth order          (K2)
+//   tile sort             CUB radix sort on the <=16-bit tile key only (2 passes, stable)     (replaces L2)
+//   ranges_kernel         per-tile [start,end)                                                 (K3)
+//   blend_forward_kernel  one warp per 8x4 pixel sub-tile, lane-parallel exact culling         (K4/K5)
+//
+// The reference sorts R (tile<<32|depth) 64-bit keys in ~6 radix passes.  Sorting the P Gaussians by
+// depth once and then stably bucketing the R instances by tile gives the IDENTICAL order (tile, depth
+// bits, ascending id) with ~6x less sort traffic.
+//
+// Backward (RAST/cuda_rasterizer/rasterizer_impl.cu:341-435):
+//   blend_backward_kernel       back-to-front re-walk, butterfly warp reduction, 9 atomics per
+//                               (warp, Gaussian) instead of 9 per (pixel, Gaussian)              (K6)
+//   preprocess_backward_kernel  conic/mean2D/colour gradients -> all dense per-Gaussian outputs  (K7+K8 fused)
+#include <cuda_runtime.h>
+#include <cub/cub.cuh>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/lgrast.h"
+#include "lgr_math.cuh"
+
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int ACC_STRIDE = 12;  // floats per Gaussian in the backward accumulator record
+// record layout: 0..2 dL/dcolor rgb | 3 dL/dopacity | 4,5 dL/dmean2D xy | 6,7,8 dL/dconic x,y,w | 9..11 pad
+
+thread_local std::string g_last_error;
+std::atomic<uint64_t> g_launches{0};
+
+// ---- optional per-stage device timing (CUDA events on the launch stream), used by bench.py's roofline ----
+enum StageId { ST_PREPROCESS = 0, ST_DEPTH_SORT, ST_SCAN, ST_EMIT, ST_TILE_SORT, ST_RANGES, ST_BLEND_FWD, ST_BLEND_FWD_COUNT,
+               ST_SCORE, ST_BLEND_BWD, ST_PREPROCESS_BWD, ST_MEMSET, ST_COUNT };
+const char* const kStageNames[ST_COUNT] = {"preprocess_kernel", "depth_sort(cub)", "scan(cub)", "emit_kernel", "tile_sort(cub)",
+                                           "ranges_kernel", "blend_forward_kernel", "blend_forward_kernel<count>", "score_kernel",
+                                           "blend_backward_kernel", "preprocess_backward_kernel", "memset"};
+struct ProfRecord { int stage; cudaEvent_t a, b; };
+bool g_prof_on = false;
+std::vector<ProfRecord> g_prof_records;
+std::vector<cudaEvent_t> g_prof_pool;
+double g_prof_ms[ST_COUNT] = {0};
+uint64_t g_prof_n[ST_COUNT] = {0};
+std::mutex g_prof_mutex;
+
+cudaEvent_t prof_event()
+{
+    if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+struct ProfScope {
+    int stage; cudaStream_t s; cudaEvent_t a = nullptr, b = nullptr; bool on;
+    ProfScope(int stage_, cudaStream_t s_) : stage(stage_), s(s_), on(g_prof_on)
+    {
+        if (on) { std::lock_guard<std::mutex> l(g_prof_mutex); a = prof_event(); b = prof_event(); cudaEventRecord(a, s); }
+    }
+    ~ProfScope()
+    {
+        if (on) { cudaEventRecord(b, s); std::lock_guard<std::mutex> l(g_prof_mutex); g_prof_records.push_back({stage, a, b}); }
+    }
+};
+
+#define LGR_CUDA_TRY(expr)                                                                          \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess) {                                                                    \
+            g_last_error = std::string(#expr) + ": " + cudaGetErrorString(_e);                      \
+            return LGR_ERR_CUDA;                                                                    \
+        }                                                                                           \
+    } while (0)
+
+#define LGR_LAUNCH_CHECK(name, debug, stream)                                                       \
+    do {                                                                                            \
+        g_launches.fetch_add(1, std::memory_order_relaxed);                                         \
+        cudaError_t _e = cudaGetLastError();                                                        \
+        if (_e == cudaSuccess && (debug)) _e = cudaStreamSynchronize(stream);                       \
+        if (_e != cudaSuccess) {                                                                    \
+            g_last_error = std::string(name) + ": " + cudaGetErrorString(_e);                       \
+            return LGR_ERR_CUDA;                                                                    \
+        }                                                                                           \
+    } while (0)
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Sub-allocation of one opaque blob (the role of obtain()/required() in
+// RAST/cuda_rasterizer/rasterizer_impl.h:21-73).  With base == nullptr it only measures.
+struct Carver {
+    char* base;
+    size_t off = 0;
+    explicit Carver(char* b) : base(b) {}
+    template <typename T>
+    T* take(size_t count, size_t* offset_out = nullptr)
+    {
+        off = align_up(off, 256);
+        if (offset_out) *offset_out = off;
+        T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+        off += count * sizeof(T);
+        return p;
+    }
+};
+
+struct GeometryState {
+    float* depth;              // [P] view-space z (valid where radii > 0)
+    float2* means2D;           // [P]
+    float4* conic_opacity;     // [P]
+    float4* rgb;               // [P] xyz = colour fed to the blend
+    float* cov3D;              // [6P]
+    uint8_t* clamped;          // [P] bit c = channel c clamped
+    uint32_t* tiles_touched;   // [P]
+    uint32_t* sorted_ids;      // [P] Gaussian ids in (depth bits, id) order; culled ones last
+    uint32_t* depth_keys;      // [P] scratch
+    uint32_t* depth_keys_sorted;  // [P] scratch
+    uint32_t* iota;            // [P] scratch
+    uint32_t* offsets;         // [P] inclusive scan of tiles_touched in sorted order
+    float* grad_acc;           // [12P] backward accumulator records
+    int* num_rendered;         // [1]
+    char* cub_temp;
+    size_t cub_temp_bytes;
+    size_t offs[8];
+    size_t total;
+};
+
+struct TilesTouchedOp {
+    const uint32_t* tiles;
+    __host__ __device__ __forceinline__ uint32_t operator()(const uint32_t& id) const { return tiles[id]; }
+};
+
+GeometryState carve_geometry(char* base, size_t P)
+{
+    GeometryState g;
+    Carver c(base);
+    g.num_rendered = c.take<int>(64);
+    g.depth = c.take<float>(P, &g.offs[0]);
+    g.means2D = c.take<float2>(P, &g.offs[1]);
+    g.conic_opacity = c.take<float4>(P, &g.offs[2]);
+    g.rgb = c.take<float4>(P, &g.offs[3]);
+    g.cov3D = c.take<float>(6 * P, &g.offs[4]);
+    g.clamped = c.take<uint8_t>(P, &g.offs[5]);
+    g.tiles_touched = c.take<uint32_t>(P, &g.offs[6]);
+    g.sorted_ids = c.take<uint32_t>(P, &g.offs[7]);
+    g.depth_keys = c.take<uint32_t>(P);
+    g.depth_keys_sorted = c.take<uint32_t>(P);
+    g.iota = c.take<uint32_t>(P);
+    g.offsets = c.take<uint32_t>(P);
+    g.grad_acc = c.take<float>(ACC_STRIDE * P);
+    size_t sort_bytes = 0, scan_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr,
+                                    (uint32_t*)nullptr, (int)P, 0, 32);
+    cub::TransformInputIterator<uint32_t, TilesTouchedOp, const uint32_t*> it(nullptr, TilesTouchedOp{nullptr});
+    cub::DeviceScan::InclusiveSum(nullptr, scan_bytes, it, (uint32_t*)nullptr, (int)P);
+    g.cub_temp_bytes = sort_bytes > scan_bytes ? sort_bytes : scan_bytes;
+    g.cub_temp = c.take<char>(g.cub_temp_bytes);
+    g.total = align_up(c.off, 256);
+    return g;
+}
+
+struct ImageState {
+    float* final_T;       // [N]
+    uint32_t* n_contrib;  // [N]
+    uint2* ranges;        // [tiles]
+    size_t offs[3];
+    size_t total;
+};
+
+ImageState carve_image(char* base, int W, int H)
+{
+    ImageState s;
+    const size_t N = (size_t)W * H;
+    const size_t tiles = (size_t)((W + LGR_TILE - 1) / LGR_TILE) * ((H + LGR_TILE - 1) / LGR_TILE);
+    Carver c(base);
+    s.final_T = c.take<float>(N, &s.offs[0]);
+    s.n_contrib = c.take<uint32_t>(N, &s.offs[1]);
+    s.ranges = c.take<uint2>(tiles, &s.offs[2]);
+    s.total = align_up(c.off, 256);
+    return s;
+}
+
+inline int tile_key_bits(int W, int H)
+{
+    const uint32_t tiles = (uint32_t)((W + LGR_TILE - 1) / LGR_TILE) * ((H + LGR_TILE - 1) / LGR_TILE);
+    int bits = 1;
+    while ((1u << bits) < tiles) bits++;
+    return bits;
+}
+
+struct BinningState {
+    uint32_t* point_list;       // [R] sorted ids
+    uint32_t* ids_unsorted;     // [R]
+    void* keys_unsorted;        // [R] u16 or u32 tile index
+    void* keys_sorted;          // [R]
+    char* cub_temp;
+    size_t cub_temp_bytes;
+    bool wide_keys;
+    size_t offs[1];
+    size_t total;
+};
+
+BinningState carve_binning(char* base, size_t R, int W, int H)
+{
+    BinningState b;
+    const int bits = tile_key_bits(W, H);
+    b.wide_keys = bits > 16;
+    const size_t Rn = R ? R : 1;
+    Carver c(base);
+    b.point_list = c.take<uint32_t>(Rn, &b.offs[0]);
+    b.ids_unsorted = c.take<uint32_t>(Rn);
+    const size_t ksz = b.wide_keys ? 4 : 2;
+    b.keys_unsorted = c.take<char>(Rn * ksz);
+    b.keys_sorted = c.take<char>(Rn * ksz);
+    size_t bytes = 0;
+    if (b.wide_keys)
+        cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr,
+                                        (uint32_t*)nullptr, (int)Rn, 0, bits);
+    else
+        cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint16_t*)nullptr, (uint16_t*)nullptr, (const uint32_t*)nullptr,
+                                        (uint32_t*)nullptr, (int)Rn, 0, bits);
+    b.cub_temp_bytes = bytes;
+    b.cub_temp = c.take<char>(bytes);
+    b.total = align_up(c.off, 256);
+    return b;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1  preprocess
+// ------------------------------------------------------------------------------------------------
+struct PreprocessArgs {
+    int P, D, M, W, H, gx, gy;
+    float fx, fy, tanx, tany, mod;
+    const float* means3D;
+    const float* scales;
+    const float* rotations;
+    const float* opacities;
+    const float* shs;
+    const float* cov3D_precomp;
+    const float* colors_precomp;
+    const float* view;
+    const float* proj;
+    const float* campos;
+    int prefiltered;
+};
+
+__global__ void __launch_bounds__(256) preprocess_kernel(PreprocessArgs a, int* __restrict__ radii, GeometryState g)
+{
+    __shared__ float s_cam[36];  // view 16 | proj 16 | campos 3
+    if (threadIdx.x < 16) s_cam[threadIdx.x] = a.view[threadIdx.x];
+    else if (threadIdx.x < 32) s_cam[threadIdx.x] = a.proj[threadIdx.x - 16];
+    else if (threadIdx.x < 35) s_cam[threadIdx.x] = a.campos[threadIdx.x - 32];
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.P) return;
+    const float* view = s_cam;
+    const float* proj = s_cam + 16;
+    const float* cam = s_cam + 32;
+
+    const float x = a.means3D[3 * i], y = a.means3D[3 * i + 1], z = a.means3D[3 * i + 2];
+    float cov[6];
+    bool have_cov = false;
+    // the cull test needs only the position; do it before touching scale/rot
+    const float depth0 = lgr::xform_row(view, 2, x, y, z);
+    bool visible = depth0 > 0.2f;
+    lgr::Geom geo;
+    if (visible) {
+        if (a.cov3D_precomp) {
+#pragma unroll
+            for (int k = 0; k < 6; k++) cov[k] = a.cov3D_precomp[6 * (size_t)i + k];
+        } else {
+            const float4 q = reinterpret_cast<const float4*>(a.rotations)[i];
+            lgr::cov3d_from_scale_rot(a.scales[3 * i], a.scales[3 * i + 1], a.scales[3 * i + 2], a.mod, q.x, q.y, q.z, q.w, cov);
+            have_cov = true;
+        }
+        visible = lgr::project_gaussian(x, y, z, view, proj, cov, a.fx, a.fy, a.tanx, a.tany, a.W, a.H, a.gx, a.gy, geo);
+    } else if (a.prefiltered) {
+        printf("Point is filtered although prefiltered is set. This shouldn't happen!");
+        __trap();
+    }
+    g.iota[i] = (uint32_t)i;
+    if (have_cov) {  // the reference stores cov3D before the later culls (forward.cu:213)
+#pragma unroll
+        for (int k = 0; k < 6; k++) g.cov3D[6 * (size_t)i + k] = cov[k];
+    }
+    if (!visible) {
+        radii[i] = 0;
+        g.tiles_touched[i] = 0;
+        g.depth_keys[i] = 0xffffffffu;
+        g.clamped[i] = 0;
+        return;
+    }
+    float rgb[3];
+    unsigned clamp_bits = 0;
+    if (a.colors_precomp) {
+        rgb[0] = a.colors_precomp[3 * (size_t)i];
+        rgb[1] = a.colors_precomp[3 * (size_t)i + 1];
+        rgb[2] = a.colors_precomp[3 * (size_t)i + 2];
+    } else {
+        const float* sh = a.shs + (size_t)i * a.M * 3;
+        if (a.M == 16) {  // 192 B per Gaussian, 16 B aligned: 128-bit loads of the active prefix only
+            float v[48];
+            const int nfl = 3 * (a.D + 1) * (a.D + 1);
+            const float4* s4 = reinterpret_cast<const float4*>(sh);
+#pragma unroll
+            for (int j = 0; j < 12; j++) {
+                float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (4 * j < nfl) t = __ldg(s4 + j);
+                v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+            }
+            lgr::sh_to_rgb(a.D, [&](int k) { return v[k]; }, x, y, z, cam, rgb, clamp_bits);
+        } else {
+            lgr::sh_to_rgb(a.D, [&](int k) { return __ldg(sh + k); }, x, y, z, cam, rgb, clamp_bits);
+        }
+    }
+    radii[i] = geo.radius;
+    g.depth[i] = geo.depth;
+    g.depth_keys[i] = __float_as_uint(geo.depth);
+    g.means2D[i] = make_float2(geo.px, geo.py);
+    g.conic_opacity[i] = make_float4(geo.conic_x, geo.conic_y, geo.conic_z, a.opacities[i]);
+    g.rgb[i] = make_float4(rgb[0], rgb[1], rgb[2], 0.f);
+    g.clamped[i] = (uint8_t)clamp_bits;
+    g.tiles_touched[i] = (uint32_t)((geo.rect.y1 - geo.rect.y0) * (geo.rect.x1 - geo.rect.x0));
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2  emit (tile, id) instances in depth order     (RAST/cuda_rasterizer/rasterizer_impl.cu:70-111)
+// ------------------------------------------------------------------------------------------------
+template <typename KeyT>
+__global__ void __launch_bounds__(256) emit_kernel(int P, const uint32_t* __restrict__ sorted_ids, const uint32_t* __restrict__ offsets,
+                                                   const uint32_t* __restrict__ tiles_touched, const float2* __restrict__ means2D,
+                                                   const int* __restrict__ radii, int gx, int gy, KeyT* __restrict__ keys,
+                                                   uint32_t* __restrict__ ids)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= P) return;
+    const uint32_t id = sorted_ids[k];
+    if (tiles_touched[id] == 0) return;
+    uint32_t off = (k == 0) ? 0u : offsets[k - 1];
+    const float2 p = means2D[id];
+    const lgr::TileRect r = lgr::tile_rect(p.x, p.y, radii[id], gx, gy);
+    for (int ty = r.y0; ty < r.y1; ty++)
+        for (int tx = r.x0; tx < r.x1; tx++) {
+            keys[off] = (KeyT)(ty * gx + tx);
+            ids[off] = id;
+            off++;
+        }
+}
+
+// K3  per-tile ranges from the sorted tile keys    (RAST/cuda_rasterizer/rasterizer_impl.cu:116-138)
+template <typename KeyT>
+__global__ void __launch_bounds__(256) ranges_kernel(int R, const KeyT* __restrict__ keys, uint2* __restrict__ ranges)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= R) return;
+    const uint32_t t = keys[k];
+    if (k == 0) ranges[t].x = 0;
+    else {
+        const uint32_t prev = keys[k - 1];
+        if (prev != t) {
+            ranges[prev].y = k;
+            ranges[t].x = k;
+        }
+    }
+    if (k == R - 1) ranges[t].y = R;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Exact, conservative sub-tile culling.  Returns true when NO pixel centre in [rx0,rx1]x[ry0,ry1] can
+// reach alpha >= 1/255 for this Gaussian, i.e. when the reference would skip every pair at
+// RAST/cuda_rasterizer/forward.cu:345-347.  A 1% margin on alpha covers all rounding in this test.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool subtile_cull(float gxp, float gyp, float4 co, float rx0, float rx1, float ry0, float ry1)
+{
+    const float A = co.x, B = co.y, Cc = co.z;
+    const float t = 257.55f * co.w;  // 255 * 1.01 * opacity
+    if (t <= 1.0f) return true;      // alpha <= opacity < 1/255 everywhere
+    const float dx_lo = gxp - rx1, dx_hi = gxp - rx0, dy_lo = gyp - ry1, dy_hi = gyp - ry0;
+    const float cx = fminf(fmaxf(0.f, dx_lo), dx_hi), cy = fminf(fmaxf(0.f, dy_lo), dy_hi);
+    if (cx == 0.f && cy == 0.f) return false;                        // centre inside the sub-tile
+    if (!(A > 0.f && Cc > 0.f && A * Cc - B * B > 0.f)) return false;  // not positive definite: never cull
+    const float thr = __logf(t);
+    float qmin = 3.0e38f;
+    if (cx != 0.f) {
+        const float dy = fminf(fmaxf(__fdividef(-B * cx, Cc), dy_lo), dy_hi);
+        qmin = 0.5f * (A * cx * cx + Cc * dy * dy) + B * cx * dy;
+    }
+    if (cy != 0.f) {
+        const float dx = fminf(fmaxf(__fdividef(-B * cy, A), dx_lo), dx_hi);
+        qmin = fminf(qmin, 0.5f * (A * dx * dx + Cc * cy * cy) + B * dx * cy);
+    }
+    return qmin > thr;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4/K5  forward blend.  Block = one 16x16 tile, 8 warps; warp w owns the 8x4 pixel sub-tile
+// (w&1, w>>1).  Warps never synchronise with each other: each walks the tile's depth-sorted list in
+// batches of 32 (lane-parallel gather + cull), then broadcasts the survivors through its private
+// shared-memory slice.  Per-pixel arithmetic is the reference's, operation for operation.
+// ------------------------------------------------------------------------------------------------
+template <bool COUNT>
+__global__ void __launch_bounds__(256)
+blend_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H, int tiles_x,
+                     const float2* __restrict__ means2D, const float4* __restrict__ conic_opacity, const float4* __restrict__ rgb,
+                     const float* __restrict__ bg, float* __restrict__ final_T, uint32_t* __restrict__ n_contrib,
+                     float* __restrict__ out_color, int* __restrict__ count)
+{
+    __shared__ float2 s_xy[8][32];
+    __shared__ float4 s_co[8][32];
+    __shared__ float4 s_rgb[8][32];
+    __shared__ uint32_t s_id[8][32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = blockIdx.x;
+    const int tx = tile % tiles_x, ty = tile / tiles_x;
+    const int sx0 = tx * LGR_TILE + (warp & 1) * 8, sy0 = ty * LGR_TILE + (warp >> 1) * 4;
+    const int px = sx0 + (lane & 7), py = sy0 + (lane >> 3);
+    const bool inside = px < W && py < H;
+    const float pxf = (float)px, pyf = (float)py;
+    const float rx0 = (float)sx0, rx1 = (float)min(sx0 + 7, W - 1), ry0 = (float)sy0, ry1 = (float)min(sy0 + 3, H - 1);
+    const uint2 range = ranges[tile];
+
+    float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
+    uint32_t last = 0;
+    bool done = !inside;
+
+    for (uint32_t base = range.x; base < range.y; base += 32) {
+        if (__all_sync(FULL, done)) break;
+        const uint32_t idx = base + lane;
+        const bool valid = idx < range.y;
+        const uint32_t id = valid ? point_list[idx] : 0u;
+        const float2 xy = means2D[id];
+        const float4 co = conic_opacity[id];
+        const bool keep = valid && !subtile_cull(xy.x, xy.y, co, rx0, rx1, ry0, ry1);
+        unsigned mask = __ballot_sync(FULL, keep);
+        if (mask == 0) continue;
+        float4 col = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (keep) col = rgb[id];
+        __syncwarp();
+        s_xy[warp][lane] = xy;
+        s_co[warp][lane] = co;
+        s_rgb[warp][lane] = col;
+        if (COUNT) s_id[warp][lane] = id;
+        __syncwarp();
+        while (mask) {
+            const int j = __ffs(mask) - 1;
+            mask &= mask - 1;
+            bool contrib = false;
+            if (!done) {
+                const float2 g = s_xy[warp][j];
+                const float4 c = s_co[warp][j];
+                const float dx = LGR_SUB(g.x, pxf), dy = LGR_SUB(g.y, pyf);
+                const float power = lgr::pair_power(dx, dy, c.x, c.y, c.z);
+                if (!(power > 0.0f)) {
+                    const float alpha = fminf(0.99f, LGR_MUL(c.w, expf(power)));
+                    if (!(alpha < 1.0f / 255.0f)) {
+                        const float test_T = LGR_MUL(T, LGR_SUB(1.0f, alpha));
+                        if (test_T < 0.0001f) {
+                            done = true;
+                        } else {
+                            const float4 f = s_rgb[warp][j];
+                            C0 = LGR_FMA(T, LGR_MUL(alpha, f.x), C0);
+                            C1 = LGR_FMA(T, LGR_MUL(alpha, f.y), C1);
+                            C2 = LGR_FMA(T, LGR_MUL(alpha, f.z), C2);
+                            T = test_T;
+                            last = (base - range.x) + (uint32_t)j + 1u;
+                            contrib = true;
+                        }
+                    }
+                }
+            }
+            if (COUNT) {
+                const unsigned cm = __ballot_sync(FULL, contrib);
+                if (cm != 0 && lane == 0) atomicAdd(&count[s_id[warp][j]], __popc(cm));
+            }
+            if (__all_sync(FULL, done)) mask = 0;
+        }
+    }
+    if (inside) {
+        const size_t pix = (size_t)py * W + px;
+        const size_t plane = (size_t)H * W;
+        final_T[pix] = T;
+        n_contrib[pix] = last;
+        out_color[pix] = LGR_FMA(bg[0], T, C0);
+        out_color[plane + pix] = LGR_FMA(bg[1], T, C1);
+        out_color[2 * plane + pix] = LGR_FMA(bg[2], T, C2);
+    }
+}
+
+__global__ void __launch_bounds__(256) score_kernel(int P, const int* __restrict__ count, const float* __restrict__ opacities,
+                                                    float* __restrict__ score)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < P) score[i] = opacities[i] * (float)count[i];
+}
+
+__global__ void __launch_bounds__(256) mark_visible_kernel(int P, const float* __restrict__ means3D, const float* __restrict__ view,
+                                                           uint8_t* __restrict__ present)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    float v[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) v[k] = view[k];
+    present[i] = lgr::xform_row(v, 2, means3D[3 * i], means3D[3 * i + 1], means3D[3 * i + 2]) > 0.2f;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K6  backward blend (RAST/cuda_rasterizer/backward.cu:399-557).
+// Eight gradient components are summed over the warp with a halving butterfly (9 shuffles instead of
+// 40), the ninth with a plain 5-step butterfly; then nine lanes issue one atomic each into the
+// Gaussian's 48-byte accumulator record.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void warp_accumulate9(float v0, float v1, float v2, float v3, float v4, float v5, float v6, float v7, float v8,
+                                                 float* __restrict__ rec, int lane)
+{
+    // 8 -> 4 (xor 16)
+    {
+        const bool hi = lane & 16;
+        const float s0 = hi ? v0 : v4, s1 = hi ? v1 : v5, s2 = hi ? v2 : v6, s3 = hi ? v3 : v7;
+        const float k0 = hi ? v4 : v0, k1 = hi ? v5 : v1, k2 = hi ? v6 : v2, k3 = hi ? v7 : v3;
+        v0 = k0 + __shfl_xor_sync(FULL, s0, 16);
+        v1 = k1 + __shfl_xor_sync(FULL, s1, 16);
+        v2 = k2 + __shfl_xor_sync(FULL, s2, 16);
+        v3 = k3 + __shfl_xor_sync(FULL, s3, 16);
+    }
+    // 4 -> 2 (xor 8)
+    {
+        const bool hi = lane & 8;
+        const float s0 = hi ? v0 : v2, s1 = hi ? v1 : v3;
+        const float k0 = hi ? v2 : v0, k1 = hi ? v3 : v1;
+        v0 = k0 + __shfl_xor_sync(FULL, s0, 8);
+        v1 = k1 + __shfl_xor_sync(FULL, s1, 8);
+    }
+    // 2 -> 1 (xor 4)
+    {
+        const bool hi = lane & 4;
+        const float s0 = hi ? v0 : v1;
+        const float k0 = hi ? v1 : v0;
+        v0 = k0 + __shfl_xor_sync(FULL, s0, 4);
+    }
+    v0 += __shfl_xor_sync(FULL, v0, 2);
+    v0 += __shfl_xor_sync(FULL, v0, 1);
+    v8 += __shfl_xor_sync(FULL, v8, 16);
+    v8 += __shfl_xor_sync(FULL, v8, 8);
+    v8 += __shfl_xor_sync(FULL, v8, 4);
+    v8 += __shfl_xor_sync(FULL, v8, 2);
+    v8 += __shfl_xor_sync(FULL, v8, 1);
+    // lane holds component idx = 4*bit4 + 2*bit3 + bit2 of the 8; components 0..2 colour, 3,4 mean2D, 5,6,7 conic
+    const int idx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+    const int slot = idx < 3 ? idx : idx + 1;  // skip slot 3 (opacity)
+    if ((lane & 3) == 0) atomicAdd(rec + slot, v0);
+    else if (lane == 1) atomicAdd(rec + 3, v8);
+}
+
+__global__ void __launch_bounds__(256)
+blend_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H, int tiles_x,
+                      const float2* __restrict__ means2D, const float4* __restrict__ conic_opacity, const float4* __restrict__ rgb,
+                      const float* __restrict__ bg, const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib,
+                      const float* __restrict__ dL_dpix, float* __restrict__ acc)
+{
+    __shared__ float2 s_xy[8][32];
+    __shared__ float4 s_co[8][32];
+    __shared__ float4 s_rgb[8][32];
+    __shared__ uint32_t s_id[8][32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = blockIdx.x;
+    const int tx = tile % tiles_x, ty = tile / tiles_x;
+    const int sx0 = tx * LGR_TILE + (warp & 1) * 8, sy0 = ty * LGR_TILE + (warp >> 1) * 4;
+    const int px = sx0 + (lane & 7), py = sy0 + (lane >> 3);
+    const bool inside = px < W && py < H;
+    const float pxf = (float)px, pyf = (float)py;
+    const float rx0 = (float)sx0, rx1 = (float)min(sx0 + 7, W - 1), ry0 = (float)sy0, ry1 = (float)min(sy0 + 3, H - 1);
+    const uint2 range = ranges[tile];
+    const size_t pix = (size_t)py * W + px;
+    const size_t plane = (size_t)H * W;
+
+    const float T_final = inside ? final_T[pix] : 0.f;
+    float T = T_final;
+    const uint32_t last = inside ? n_contrib[pix] : 0u;
+    float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+    if (inside) {
+        d0 = dL_dpix[pix];
+        d1 = dL_dpix[plane + pix];
+        d2 = dL_dpix[2 * plane + pix];
+    }
+    const float bg_dot = bg[0] * d0 + bg[1] * d1 + bg[2] * d2;
+    const uint32_t max_last = __reduce_max_sync(FULL, last);
+    if (max_last == 0) return;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;       // accum_rec
+    float lc0 = 0.f, lc1 = 0.f, lc2 = 0.f;    // last colour
+    float last_alpha = 0.f;
+    const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
+
+    for (int b = (int)((max_last - 1) >> 5); b >= 0; --b) {
+        const uint32_t pos = (uint32_t)b * 32u + lane;
+        const bool valid = pos < max_last;
+        const uint32_t id = valid ? point_list[range.x + pos] : 0u;
+        const float2 xy = means2D[id];
+        const float4 co = conic_opacity[id];
+        const bool keep = valid && !subtile_cull(xy.x, xy.y, co, rx0, rx1, ry0, ry1);
+        unsigned mask = __ballot_sync(FULL, keep);
+        if (mask == 0) continue;
+        float4 col = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (keep) col = rgb[id];
+        __syncwarp();
+        s_xy[warp][lane] = xy;
+        s_co[warp][lane] = co;
+        s_rgb[warp][lane] = col;
+        s_id[warp][lane] = id;
+        __syncwarp();
+        while (mask) {
+            const int j = 31 - __clz(mask);  // back to front
+            mask &= ~(1u << j);
+            const uint32_t pj = (uint32_t)b * 32u + (uint32_t)j;
+            const float2 g = s_xy[warp][j];
+            const float4 c = s_co[warp][j];
+            const float dx = LGR_SUB(g.x, pxf), dy = LGR_SUB(g.y, pyf);
+            const float power = lgr::pair_power(dx, dy, c.x, c.y, c.z);
+            float G = 0.f, alpha = 0.f;
+            bool on = (pj < last) && !(power > 0.0f);
+            if (on) {
+                G = expf(power);
+                alpha = fminf(0.99f, LGR_MUL(c.w, G));
+                on = !(alpha < 1.0f / 255.0f);
+            }
+            if (!__any_sync(FULL, on)) continue;
+            float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f, v4 = 0.f, v5 = 0.f, v6 = 0.f, v7 = 0.f, v8 = 0.f;
+            if (on) {
+                const float4 f = s_rgb[warp][j];
+                const float one_m_a = 1.0f - alpha;
+                T = T / one_m_a;
+                const float w = alpha * T;
+                a0 = last_alpha * lc0 + (1.f - last_alpha) * a0;
+                a1 = last_alpha * lc1 + (1.f - last_alpha) * a1;
+                a2 = last_alpha * lc2 + (1.f - last_alpha) * a2;
+                lc0 = f.x; lc1 = f.y; lc2 = f.z;
+                float dL_dalpha = (f.x - a0) * d0 + (f.y - a1) * d1 + (f.z - a2) * d2;
+                v0 = w * d0; v1 = w * d1; v2 = w * d2;
+                dL_dalpha *= T;
+                last_alpha = alpha;
+                dL_dalpha += (-T_final / one_m_a) * bg_dot;
+                const float dL_dG = c.w * dL_dalpha;
+                const float gdx = G * dx, gdy = G * dy;
+                const float dG_ddelx = -gdx * c.x - gdy * c.y;
+                const float dG_ddely = -gdy * c.z - gdx * c.y;
+                v3 = dL_dG * dG_ddelx * ddelx_dx;
+                v4 = dL_dG * dG_ddely * ddely_dy;
+                v5 = -0.5f * gdx * dx * dL_dG;
+                v6 = -0.5f * gdx * dy * dL_dG;
+                v7 = -0.5f * gdy * dy * dL_dG;
+                v8 = G * dL_dalpha;
+            }
+            warp_accumulate9(v0, v1, v2, v3, v4, v5, v6, v7, v8, acc + (size_t)s_id[warp][j] * ACC_STRIDE, lane);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K7+K8 fused  (RAST/cuda_rasterizer/backward.cu:144-396).  One thread per Gaussian; writes EVERY dense
+// output row (zeros for culled Gaussians) so the caller never has to clear them.
+// ------------------------------------------------------------------------------------------------
+struct PreBackArgs {
+    int P, D, M, W, H;
+    float fx, fy, tanx, tany, mod;
+    const float* means3D;
+    const float* scales;
+    const float* rotations;
+    const float* shs;
+    const float* cov3D;  // precomputed by the caller, or the forward's geometry cov3D
+    const float* view;
+    const float* proj;
+    const float* campos;
+    const int* radii;
+    const uint8_t* clamped;
+    const float* acc;
+    float* dL_dmeans2D;
+    float* dL_dcolors;
+    float* dL_dopacity;
+    float* dL_dmeans3D;
+    float* dL_dcov3D;
+    float* dL_dsh;
+    float* dL_dscales;
+    float* dL_drot;
+};
+
+__global__ void __launch_bounds__(256) preprocess_backward_kernel(PreBackArgs a)
+{
+    __shared__ float s_cam[36];
+    if (threadIdx.x < 16) s_cam[threadIdx.x] = a.view[threadIdx.x];
+    else if (threadIdx.x < 32) s_cam[threadIdx.x] = a.proj[threadIdx.x - 16];
+    else if (threadIdx.x < 35) s_cam[threadIdx.x] = a.campos[threadIdx.x - 32];
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.P) return;
+    const size_t si = (size_t)i;
+    const bool vis = a.radii[i] > 0;
+    float4* dsh4 = a.M == 16 ? reinterpret_cast<float4*>(a.dL_dsh + si * 48) : nullptr;
+    if (!vis) {
+        a.dL_dmeans2D[3 * si] = 0.f; a.dL_dmeans2D[3 * si + 1] = 0.f; a.dL_dmeans2D[3 * si + 2] = 0.f;
+        a.dL_dcolors[3 * si] = 0.f; a.dL_dcolors[3 * si + 1] = 0.f; a.dL_dcolors[3 * si + 2] = 0.f;
+        a.dL_dopacity[si] = 0.f;
+        a.dL_dmeans3D[3 * si] = 0.f; a.dL_dmeans3D[3 * si + 1] = 0.f; a.dL_dmeans3D[3 * si + 2] = 0.f;
+#pragma unroll
+        for (int k = 0; k < 6; k++) a.dL_dcov3D[6 * si + k] = 0.f;
+        a.dL_dscales[3 * si] = 0.f; a.dL_dscales[3 * si + 1] = 0.f; a.dL_dscales[3 * si + 2] = 0.f;
+        reinterpret_cast<float4*>(a.dL_drot)[si] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a.dL_dsh) {
+            if (dsh4) {
+#pragma unroll
+                for (int j = 0; j < 12; j++) dsh4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            } else {
+                for (int k = 0; k < 3 * a.M; k++) a.dL_dsh[si * 3 * a.M + k] = 0.f;
+            }
+        }
+        return;
+    }
+    const float* view = s_cam;
+    const float* proj = s_cam + 16;
+    const float* cam = s_cam + 32;
+    const float4* rec4 = reinterpret_cast<const float4*>(a.acc + si * ACC_STRIDE);
+    const float4 r0 = rec4[0], r1 = rec4[1], r2 = rec4[2];
+    // r0 = (dcol.r, dcol.g, dcol.b, dopacity)  r1 = (dmean2D.x, dmean2D.y, dconic.x, dconic.y)  r2.x = dconic.w
+    const float x = a.means3D[3 * si], y = a.means3D[3 * si + 1], z = a.means3D[3 * si + 2];
+    float c3[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) c3[k] = a.cov3D[6 * si + k];
+    float dcov[6], dmean[3];
+    lgr::cov2d_backward(x, y, z, view, c3, a.fx, a.fy, a.tanx, a.tany, r1.z, r1.w, r2.x, dcov, dmean);
+    lgr::mean2d_backward(x, y, z, proj, r1.x, r1.y, dmean);
+    a.dL_dmeans2D[3 * si] = r1.x; a.dL_dmeans2D[3 * si + 1] = r1.y; a.dL_dmeans2D[3 * si + 2] = 0.f;
+    a.dL_dcolors[3 * si] = r0.x; a.dL_dcolors[3 * si + 1] = r0.y; a.dL_dcolors[3 * si + 2] = r0.z;
+    a.dL_dopacity[si] = r0.w;
+#pragma unroll
+    for (int k = 0; k < 6; k++) a.dL_dcov3D[6 * si + k] = dcov[k];
+
+    if (a.shs) {
+        const unsigned cb = a.clamped[i];
+        const float dRGB[3] = {(cb & 1u) ? 0.f : r0.x, (cb & 2u) ? 0.f : r0.y, (cb & 4u) ? 0.f : r0.z};
+        const float* sh = a.shs + si * a.M * 3;
+        if (a.M == 16) {
+            float v[48], o[48];
+            const int nfl = 3 * (a.D + 1) * (a.D + 1);
+            const float4* s4 = reinterpret_cast<const float4*>(sh);
+#pragma unroll
+            for (int j = 0; j < 12; j++) {
+                float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (4 * j < nfl) t = __ldg(s4 + j);
+                v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+            }
+#pragma unroll
+            for (int k = 0; k < 48; k++) o[k] = 0.f;
+            lgr::sh_backward(a.D, [&](int k) { return v[k]; }, [&](int k, int c, float val) { o[3 * k + c] = val; }, x, y, z, cam,
+                             dRGB, dmean);
+#pragma unroll
+            for (int j = 0; j < 12; j++) dsh4[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+        } else {
+            float* out = a.dL_dsh + si * 3 * a.M;
+            const int nb = (a.D + 1) * (a.D + 1);
+            for (int k = 3 * nb; k < 3 * a.M; k++) out[k] = 0.f;
+            lgr::sh_backward(a.D, [&](int k) { return __ldg(sh + k); }, [&](int k, int c, float val) { out[3 * k + c] = val; }, x, y, z,
+                             cam, dRGB, dmean);
+        }
+    } else if (a.dL_dsh) {
+        for (int k = 0; k < 3 * a.M; k++) a.dL_dsh[si * 3 * a.M + k] = 0.f;
+    }
+    a.dL_dmeans3D[3 * si] = dmean[0]; a.dL_dmeans3D[3 * si + 1] = dmean[1]; a.dL_dmeans3D[3 * si + 2] = dmean[2];
+    if (a.scales) {
+        const float4 q = reinterpret_cast<const float4*>(a.rotations)[si];
+        float dscale[3], dq[4];
+        lgr::cov3d_backward(a.scales[3 * si], a.scales[3 * si + 1], a.scales[3 * si + 2], a.mod, q.x, q.y, q.z, q.w, dcov, dscale, dq);
+        a.dL_dscales[3 * si] = dscale[0]; a.dL_dscales[3 * si + 1] = dscale[1]; a.dL_dscales[3 * si + 2] = dscale[2];
+        reinterpret_cast<float4*>(a.dL_drot)[si] = make_float4(dq[0], dq[1], dq[2], dq[3]);
+    } else {
+        a.dL_dscales[3 * si] = 0.f; a.dL_dscales[3 * si + 1] = 0.f; a.dL_dscales[3 * si + 2] = 0.f;
+        reinterpret_cast<float4*>(a.dL_drot)[si] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+struct PinnedInt {
+    int* p = nullptr;
+    ~PinnedInt() { if (p) cudaFreeHost(p); }
+    int* get()
+    {
+        if (!p) cudaMallocHost(&p, 64);
+        return p;
+    }
+};
+thread_local PinnedInt t_pinned;
+
+int forward_impl(const lgr_view* v, int P, int M, const float* means3D, const float* shs, const float* colors_precomp,
+                 const float* opacities, const float* scales, const float* rotations, const float* cov3D_precomp,
+                 lgr_alloc_fn geometry_alloc, void* geometry_user, lgr_alloc_fn binning_alloc, void* binning_user,
+                 lgr_alloc_fn image_alloc, void* image_user, float* out_color, int32_t* gaussians_count, float* important_score,
+                 int32_t* radii, int32_t* num_rendered, void* cuda_stream, bool count_mode)
+{
+    cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+    if (!v || P < 0 || M < 0 || !num_rendered || !out_color || !geometry_alloc || !binning_alloc || !image_alloc) {
+        g_last_error = "lgr_forward: missing required argument";
+        return LGR_ERR_INVALID_ARG;
+    }
+    const int W = v->image_width, H = v->image_height;
+    if (W <= 0 || H <= 0 || v->sh_degree < 0 || v->sh_degree > 3) {
+        g_last_error = "lgr_forward: bad image size or sh_degree";
+        return LGR_ERR_INVALID_ARG;
+    }
+    if (P > 0) {
+        if (!means3D || !opacities || !radii || (!shs && !colors_precomp) || (!cov3D_precomp && (!scales || !rotations))) {
+            g_last_error = "lgr_forward: need means3D, opacities, radii, one of shs/colors_precomp and one of scales+rotations/cov3D_precomp";
+            return LGR_ERR_INVALID_ARG;
+        }
+        if (shs && !colors_precomp && (v->sh_degree + 1) * (v->sh_degree + 1) > M) {
+            g_last_error = "lgr_forward: sh_degree needs more coefficients than M";
+            return LGR_ERR_INVALID_ARG;
+        }
+        if (count_mode && (!gaussians_count || !important_score)) {
+            g_last_error = "lgr_forward_count: gaussians_count / important_score missing";
+            return LGR_ERR_INVALID_ARG;
+        }
+    }
+    const bool debug = v->debug != 0;
+    *num_rendered = 0;
+    const int gx = (W + LGR_TILE - 1) / LGR_TILE, gy = (H + LGR_TILE - 1) / LGR_TILE;
+    const size_t N = (size_t)W * H;
+
+    if (P == 0) {  // the reference returns an all-zero image and empty blobs (rasterize_points.cu:79-93)
+        LGR_CUDA_TRY(cudaMemsetAsync(out_color, 0, sizeof(float) * 3 * N, stream));
+        return LGR_OK;
+    }
+    if (((uintptr_t)rotations & 15) || ((uintptr_t)shs & 15)) {
+        g_last_error = "lgr_forward: rotations and shs must be 16-byte aligned";
+        return LGR_ERR_INVALID_ARG;
+    }
+    GeometryState geo = carve_geometry(nullptr, (size_t)P);
+    char* geo_blob = geometry_alloc(geometry_user, geo.total);
+    if (!geo_blob) { g_last_error = "geometry allocator returned NULL"; return LGR_ERR_ALLOC; }
+    geo = carve_geometry(geo_blob, (size_t)P);
+
+    ImageState img = carve_image(nullptr, W, H);
+    char* img_blob = image_alloc(image_user, img.total);
+    if (!img_blob) { g_last_error = "image allocator returned NULL"; return LGR_ERR_ALLOC; }
+    img = carve_image(img_blob, W, H);
+    LGR_CUDA_TRY(cudaMemsetAsync(img.ranges, 0, sizeof(uint2) * (size_t)gx * gy, stream));
+
+    int R = 0;
+    BinningState bin;
+    if (P > 0) {
+        PreprocessArgs a;
+        a.P = P; a.D = v->sh_degree; a.M = M; a.W = W; a.H = H; a.gx = gx; a.gy = gy;
+        a.fy = H / (2.0f * v->tan_fovy);   // rasterizer_impl.cu:223-224
+        a.fx = W / (2.0f * v->tan_fovx);
+        a.tanx = v->tan_fovx; a.tany = v->tan_fovy; a.mod = v->scale_modifier;
+        a.means3D = means3D; a.scales = scales; a.rotations = rotations; a.opacities = opacities; a.shs = shs;
+        a.cov3D_precomp = cov3D_precomp; a.colors_precomp = colors_precomp;
+        a.view = v->viewmatrix; a.proj = v->projmatrix; a.campos = v->campos; a.prefiltered = v->prefiltered;
+        const int blocks = (P + 255) / 256;
+        {
+            ProfScope ps(ST_PREPROCESS, stream);
+            preprocess_kernel<<<blocks, 256, 0, stream>>>(a, radii, geo);
+        }
+        LGR_LAUNCH_CHECK("preprocess_kernel", debug, stream);
+
+        size_t tmp = geo.cub_temp_bytes;
+        {
+            ProfScope ps(ST_DEPTH_SORT, stream);
+            LGR_CUDA_TRY(cub::DeviceRadixSort::SortPairs(geo.cub_temp, tmp, (const uint32_t*)geo.depth_keys, geo.depth_keys_sorted,
+                                                          (const uint32_t*)geo.iota, geo.sorted_ids, P, 0, 32, stream));
+        }
+        cub::TransformInputIterator<uint32_t, TilesTouchedOp, const uint32_t*> it(geo.sorted_ids, TilesTouchedOp{geo.tiles_touched});
+        tmp = geo.cub_temp_bytes;
+        {
+            ProfScope ps(ST_SCAN, stream);
+            LGR_CUDA_TRY(cub::DeviceScan::InclusiveSum(geo.cub_temp, tmp, it, geo.offsets, P, stream));
+        }
+        int* host_R = t_pinned.get();
+        LGR_CUDA_TRY(cudaMemcpyAsync(host_R, geo.offsets + (P - 1), sizeof(int), cudaMemcpyDeviceToHost, stream));
+        LGR_CUDA_TRY(cudaStreamSynchronize(stream));
+        R = *host_R;
+    }
+    bin = carve_binning(nullptr, (size_t)R, W, H);
+    char* bin_blob = binning_alloc(binning_user, bin.total);
+    if (!bin_blob) { g_last_error = "binning allocator returned NULL"; return LGR_ERR_ALLOC; }
+    bin = carve_binning(bin_blob, (size_t)R, W, H);
+
+    if (R > 0) {
+        const int blocks = (P + 255) / 256;
+        const int bits = tile_key_bits(W, H);
+        size_t tmp = bin.cub_temp_bytes;
+        if (bin.wide_keys) {
+            {
+                ProfScope ps(ST_EMIT, stream);
+                emit_kernel<uint32_t><<<blocks, 256, 0, stream>>>(P, geo.sorted_ids, geo.offsets, geo.tiles_touched, geo.means2D, radii,
+                                                                   gx, gy, (uint32_t*)bin.keys_unsorted, bin.ids_unsorted);
+            }
+            LGR_LAUNCH_CHECK("emit_kernel", debug, stream);
+            {
+                ProfScope ps(ST_TILE_SORT, stream);
+                LGR_CUDA_TRY(cub::DeviceRadixSort::SortPairs(bin.cub_temp, tmp, (const uint32_t*)bin.keys_unsorted,
+                                                              (uint32_t*)bin.keys_sorted, (const uint32_t*)bin.ids_unsorted,
+                                                              bin.point_list, R, 0, bits, stream));
+            }
+            ProfScope ps(ST_RANGES, stream);
+            ranges_kernel<uint32_t><<<(R + 255) / 256, 256, 0, stream>>>(R, (const uint32_t*)bin.keys_sorted, img.ranges);
+        } else {
+            {
+                ProfScope ps(ST_EMIT, stream);
+                emit_kernel<uint16_t><<<blocks, 256, 0, stream>>>(P, geo.sorted_ids, geo.offsets, geo.tiles_touched, geo.means2D, radii,
+                                                                   gx, gy, (uint16_t*)bin.keys_unsorted, bin.ids_unsorted);
+            }
+            LGR_LAUNCH_CHECK("emit_kernel", debug, stream);
+            {
+                ProfScope ps(ST_TILE_SORT, stream);
+                LGR_CUDA_TRY(cub::DeviceRadixSort::SortPairs(bin.cub_temp, tmp, (const uint16_t*)bin.keys_unsorted,
+                                                              (uint16_t*)bin.keys_sorted, (const uint32_t*)bin.ids_unsorted,
+                                                              bin.point_list, R, 0, bits, stream));
+            }
+            ProfScope ps(ST_RANGES, stream);
+            ranges_kernel<uint16_t><<<(R + 255) / 256, 256, 0, stream>>>(R, (const uint16_t*)bin.keys_sorted, img.ranges);
+        }
+        LGR_LAUNCH_CHECK("ranges_kernel", debug, stream);
+    }
+    if (count_mode && P > 0) LGR_CUDA_TRY(cudaMemsetAsync(gaussians_count, 0, sizeof(int) * (size_t)P, stream));
+    {
+        const int tiles = gx * gy;
+        ProfScope ps(count_mode ? ST_BLEND_FWD_COUNT : ST_BLEND_FWD, stream);
+        if (count_mode)
+            blend_forward_kernel<true><<<tiles, 256, 0, stream>>>(img.ranges, bin.point_list, W, H, gx, geo.means2D, geo.conic_opacity,
+                                                                   geo.rgb, v->background, img.final_T, img.n_contrib, out_color,
+                                                                   gaussians_count);
+        else
+            blend_forward_kernel<false><<<tiles, 256, 0, stream>>>(img.ranges, bin.point_list, W, H, gx, geo.means2D, geo.conic_opacity,
+                                                                    geo.rgb, v->background, img.final_T, img.n_contrib, out_color,
+                                                                    nullptr);
+        LGR_LAUNCH_CHECK("blend_forward_kernel", debug, stream);
+    }
+    if (count_mode && P > 0) {
+        ProfScope ps(ST_SCORE, stream);
+        score_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, gaussians_count, opacities, important_score);
+        LGR_LAUNCH_CHECK("score_kernel", debug, stream);
+    }
+    (void)N;
+    *num_rendered = R;
+    return LGR_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int lgr_abi_version(void) { return LGR_ABI_VERSION; }
+const char* lgr_last_error(void) { return g_last_error.c_str(); }
+uint64_t lgr_launch_count(void) { return g_launches.load(); }
+
+int lgr_profile_enable(int on)
+{
+    std::lock_guard<std::mutex> l(g_prof_mutex);
+    g_prof_on = on != 0;
+    return LGR_OK;
+}
+
+int lgr_profile_stage_count(void) { return ST_COUNT; }
+const char* lgr_profile_stage_name(int k) { return (k >= 0 && k < ST_COUNT) ? kStageNames[k] : ""; }
+
+int lgr_profile_collect(double* ms_out, uint64_t* launches_out, int n)
+{
+    LGR_CUDA_TRY(cudaDeviceSynchronize());
+    std::lock_guard<std::mutex> l(g_prof_mutex);
+    for (const ProfRecord& r : g_prof_records) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+            g_prof_ms[r.stage] += ms;
+            g_prof_n[r.stage] += 1;
+        }
+        g_prof_pool.push_back(r.a);
+        g_prof_pool.push_back(r.b);
+    }
+    g_prof_records.clear();
+    for (int k = 0; k < n && k < ST_COUNT; k++) {
+        if (ms_out) ms_out[k] = g_prof_ms[k];
+        if (launches_out) launches_out[k] = g_prof_n[k];
+        g_prof_ms[k] = 0;
+        g_prof_n[k] = 0;
+    }
+    return LGR_OK;
+}
+
+size_t lgr_geometry_layout(int P, size_t* out, int n_out)
+{
+    GeometryState g = carve_geometry(nullptr, (size_t)(P > 0 ? P : 1));
+    for (int k = 0; k < n_out && k < 8; k++) out[k] = g.offs[k];
+    return g.total;
+}
+
+size_t lgr_image_layout(int width, int height, size_t* out, int n_out)
+{
+    ImageState s = carve_image(nullptr, width, height);
+    for (int k = 0; k < n_out && k < 3; k++) out[k] = s.offs[k];
+    return s.total;
+}
+
+size_t lgr_binning_layout(int num_rendered, int width, int height, size_t* out, int n_out)
+{
+    BinningState b = carve_binning(nullptr, (size_t)(num_rendered > 0 ? num_rendered : 0), width, height);
+    for (int k = 0; k < n_out && k < 1; k++) out[k] = b.offs[k];
+    return b.total;
+}
+
+int lgr_forward(const lgr_view* view, int P, int M, const float* means3D, const float* shs, const float* colors_precomp,
+                const float* opacities, const float* scales, const float* rotations, const float* cov3D_precomp,
+                lgr_alloc_fn geometry_alloc, void* geometry_user, lgr_alloc_fn binning_alloc, void* binning_user,
+                lgr_alloc_fn image_alloc, void* image_user, float* out_color, int32_t* radii, int32_t* num_rendered, void* cuda_stream)
+{
+    return forward_impl(view, P, M, means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, geometry_alloc,
+                        geometry_user, binning_alloc, binning_user, image_alloc, image_user, out_color, nullptr, nullptr, radii,
+                        num_rendered, cuda_stream, false);
+}
+
+int lgr_forward_count(const lgr_view* view, int P, int M, const float* means3D, const float* shs, const float* colors_precomp,
+                      const float* opacities, const float* scales, const float* rotations, const float* cov3D_precomp,
+                      lgr_alloc_fn geometry_alloc, void* geometry_user, lgr_alloc_fn binning_alloc, void* binning_user,
+                      lgr_alloc_fn image_alloc, void* image_user, float* out_color, int32_t* gaussians_count, float* important_score,
+                      int32_t* radii, int32_t* num_rendered, void* cuda_stream)
+{
+    return forward_impl(view, P, M, means3D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp, geometry_alloc,
+                        geometry_user, binning_alloc, binning_user, image_alloc, image_user, out_color, gaussians_count,
+                        important_score, radii, num_rendered, cuda_stream, true);
+}
+
+int lgr_backward(const lgr_view* v, int P, int M, int num_rendered, const float* means3D, const float* shs,
+                 const float* colors_precomp, const float* scales, const float* rotations, const float* cov3D_precomp,
+                 const int32_t* radii, char* geometry_blob, char* binning_blob, char* image_blob, const float* dL_dout_color,
+                 float* dL_dmeans2D, float* dL_dcolors, float* dL_dopacity, float* dL_dmeans3D, float* dL_dcov3D, float* dL_dsh,
+                 float* dL_dscales, float* dL_drotations, void* cuda_stream)
+{
+    cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+    if (P == 0) return LGR_OK;
+    if (!v || P < 0 || !means3D || !radii || !geometry_blob || !binning_blob || !image_blob || !dL_dout_color || !dL_dmeans2D ||
+        !dL_dcolors || !dL_dopacity || !dL_dmeans3D || !dL_dcov3D || !dL_dscales || !dL_drotations || (M > 0 && !dL_dsh)) {
+        g_last_error = "lgr_backward: missing required argument";
+        return LGR_ERR_INVALID_ARG;
+    }
+    (void)colors_precomp;
+    if (((uintptr_t)rotations & 15) || ((uintptr_t)shs & 15) || ((uintptr_t)dL_dsh & 15) || ((uintptr_t)dL_drotations & 15)) {
+        g_last_error = "lgr_backward: rotations, shs, dL_dsh and dL_drotations must be 16-byte aligned";
+        return LGR_ERR_INVALID_ARG;
+    }
+    const bool debug = v->debug != 0;
+    const int W = v->image_width, H = v->image_height;
+    const int gx = (W + LGR_TILE - 1) / LGR_TILE, gy = (H + LGR_TILE - 1) / LGR_TILE;
+    GeometryState geo = carve_geometry(geometry_blob, (size_t)P);
+    ImageState img = carve_image(image_blob, W, H);
+    BinningState bin = carve_binning(binning_blob, (size_t)(num_rendered > 0 ? num_rendered : 0), W, H);
+
+    {
+        ProfScope ps(ST_MEMSET, stream);
+        LGR_CUDA_TRY(cudaMemsetAsync(geo.grad_acc, 0, sizeof(float) * ACC_STRIDE * (size_t)P, stream));
+    }
+    if (num_rendered > 0) {
+        ProfScope ps(ST_BLEND_BWD, stream);
+        blend_backward_kernel<<<gx * gy, 256, 0, stream>>>(img.ranges, bin.point_list, W, H, gx, geo.means2D, geo.conic_opacity, geo.rgb,
+                                                            v->background, img.final_T, img.n_contrib, dL_dout_color, geo.grad_acc);
+        LGR_LAUNCH_CHECK("blend_backward_kernel", debug, stream);
+    }
+    PreBackArgs a;
+    a.P = P; a.D = v->sh_degree; a.M = M; a.W = W; a.H = H;
+    a.fy = H / (2.0f * v->tan_fovy);
+    a.fx = W / (2.0f * v->tan_fovx);
+    a.tanx = v->tan_fovx; a.tany = v->tan_fovy; a.mod = v->scale_modifier;
+    a.means3D = means3D; a.scales = scales; a.rotations = rotations; a.shs = shs;
+    a.cov3D = cov3D_precomp ? cov3D_precomp : geo.cov3D;
+    a.view = v->viewmatrix; a.proj = v->projmatrix; a.campos = v->campos;
+    a.radii = radii; a.clamped = geo.clamped; a.acc = geo.grad_acc;
+    a.dL_dmeans2D = dL_dmeans2D; a.dL_dcolors = dL_dcolors; a.dL_dopacity = dL_dopacity; a.dL_dmeans3D = dL_dmeans3D;
+    a.dL_dcov3D = dL_dcov3D; a.dL_dsh = dL_dsh; a.dL_dscales = dL_dscales; a.dL_drot = dL_drotations;
+    {
+        ProfScope ps(ST_PREPROCESS_BWD, stream);
+        preprocess_backward_kernel<<<(P + 255) / 256, 256, 0, stream>>>(a);
+    }
+    LGR_LAUNCH_CHECK("preprocess_backward_kernel", debug, stream);
+    return LGR_OK;
+}
+
+int lgr_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix, uint8_t* present, void* cuda_stream)
+{
+    (void)projmatrix;
+    if (P == 0) return LGR_OK;
+    if (P < 0 || !means3D || !viewmatrix || !present) {
+        g_last_error = "lgr_mark_visible: missing required argument";
+        return LGR_ERR_INVALID_ARG;
+    }
+    cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+    mark_visible_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, means3D, viewmatrix, present);
+    LGR_LAUNCH_CHECK("mark_visible_kernel", false, stream);
+    return LGR_OK;
+}
+
+}  // extern "C"

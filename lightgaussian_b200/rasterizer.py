@@ -1,0 +1,258 @@
+"""The reference's Python rasterizer surface on top of liblgrast.so.
+
+Mirrors RAST/diff_gaussian_rasterization/__init__.py (RAST = submodules/compress-diff-gaussian-rasterization):
+  GaussianRasterizationSettings  (:248-261)  same 13 fields, same order
+  GaussianRasterizer             (:263-346)  .forward / .forward_count / .markVisible / .raster_settings
+  rasterize_gaussians            (:25-59)    dispatch on raster_settings.f_count
+  _C                              pybind module of RAST/ext.cpp:15-20 -> here a namespace with the same four
+                                  callables and the same argument order / tuple layouts.
+
+Differences: launches go to torch's *current* stream on the tensors' device (the reference uses the legacy
+default stream), gradients are produced without zero-filled temporaries, and the significance outputs of
+count mode are exact and deterministic (see include/lgrast.h).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import NamedTuple
+
+import torch
+import torch.nn as nn
+
+from . import capi
+
+
+class GaussianRasterizationSettings(NamedTuple):
+    image_height: int
+    image_width: int
+    tanfovx: float
+    tanfovy: float
+    bg: torch.Tensor
+    scale_modifier: float
+    viewmatrix: torch.Tensor
+    projmatrix: torch.Tensor
+    sh_degree: int
+    campos: torch.Tensor
+    prefiltered: bool
+    debug: bool
+    f_count: bool
+
+
+_last_R = [0]
+
+
+def last_num_rendered() -> int:
+    """num_rendered of the most recent forward call in this process (diagnostics / bench.py)."""
+    return _last_R[0]
+
+
+def _f32c(t, name):
+    """contiguous float32 CUDA view of an input (None for the reference's empty 'absent' tensors)."""
+    if t is None or t.numel() == 0:
+        return None
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"{name} must be float32, got {t.dtype}")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor")
+    return t.contiguous()
+
+
+def _make_view(device, background, viewmatrix, projmatrix, campos, tan_fovx, tan_fovy, H, W, scale_modifier, degree,
+               prefiltered, debug):
+    keep = [_f32c(background, "bg"), _f32c(viewmatrix, "viewmatrix"), _f32c(projmatrix, "projmatrix"), _f32c(campos, "campos")]
+    for k, n in zip(keep, ("bg", "viewmatrix", "projmatrix", "campos")):
+        if k is None:
+            raise RuntimeError(f"{n} must be a non-empty CUDA tensor")
+    v = capi.LgrView(int(W), int(H), float(tan_fovx), float(tan_fovy), float(scale_modifier), int(degree), int(bool(prefiltered)),
+                     int(bool(debug)), keep[1].data_ptr(), keep[2].data_ptr(), keep[3].data_ptr(), keep[0].data_ptr())
+    return v, keep
+
+
+def _forward_native(count_mode, background, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp, viewmatrix,
+                    projmatrix, tan_fovx, tan_fovy, image_height, image_width, sh, degree, campos, prefiltered, debug):
+    if means3D.dim() != 2 or means3D.size(1) != 3:
+        raise RuntimeError("means3D must have dimensions (num_points, 3)")  # rasterize_points.cu:68-70
+    lib = capi.load()
+    device = means3D.device
+    if not means3D.is_cuda:
+        raise RuntimeError("means3D must be a CUDA tensor: this rasterizer has no CPU path")
+    P, H, W = means3D.size(0), int(image_height), int(image_width)
+    means3D_c = _f32c(means3D, "means3D")
+    colors_c, opacity_c = _f32c(colors, "colors_precomp"), _f32c(opacity, "opacities")
+    scales_c, rot_c, cov_c, sh_c = _f32c(scales, "scales"), _f32c(rotations, "rotations"), _f32c(cov3D_precomp, "cov3D_precomp"), _f32c(sh, "sh")
+    M = 0 if sh_c is None else sh_c.size(1)
+    out_color = torch.empty((3, H, W), dtype=torch.float32, device=device)
+    radii = torch.empty((P,), dtype=torch.int32, device=device)
+    count = score = None
+    if count_mode:
+        count = torch.empty((P,), dtype=torch.int32, device=device)
+        score = torch.empty((P,), dtype=torch.float32, device=device)
+    slots = [capi.BlobSlot(device) for _ in range(3)]
+    num_rendered = C.c_int32(0)
+    try:
+        with torch.cuda.device(device):
+            view, keep = _make_view(device, background, viewmatrix, projmatrix, campos, tan_fovx, tan_fovy, H, W, scale_modifier,
+                                    degree, prefiltered, debug)
+            stream = capi.current_stream_ptr(device)
+            common = (C.byref(view), P, M, capi.ptr(means3D_c), capi.ptr(sh_c), capi.ptr(colors_c), capi.ptr(opacity_c),
+                      capi.ptr(scales_c), capi.ptr(rot_c), capi.ptr(cov_c),
+                      capi.ALLOC_CB, slots[0].key, capi.ALLOC_CB, slots[1].key, capi.ALLOC_CB, slots[2].key)
+            if count_mode:
+                st = lib.lgr_forward_count(*common, out_color.data_ptr(), capi.ptr(count), capi.ptr(score), capi.ptr(radii),
+                                           C.byref(num_rendered), stream)
+            else:
+                st = lib.lgr_forward(*common, out_color.data_ptr(), capi.ptr(radii), C.byref(num_rendered), stream)
+        capi.check(st, "lgr_forward_count" if count_mode else "lgr_forward")
+    finally:
+        for s in slots:
+            s.release()
+    empty = lambda: torch.empty((0,), dtype=torch.uint8, device=device)  # noqa: E731
+    geom, binning, img = (s.tensor if s.tensor is not None else empty() for s in slots)
+    _last_R[0] = int(num_rendered.value)
+    if P == 0:
+        radii = torch.zeros((0,), dtype=torch.int32, device=device)
+    return count, score, int(num_rendered.value), out_color, radii, geom, binning, img
+
+
+class _NativeModule:
+    """Stand-in for the reference's pybind module `diff_gaussian_rasterization._C` (RAST/ext.cpp:15-20)."""
+
+    @staticmethod
+    def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp, viewmatrix,
+                            projmatrix, tan_fovx, tan_fovy, image_height, image_width, sh, degree, campos, prefiltered, debug):
+        r = _forward_native(False, background, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp, viewmatrix,
+                            projmatrix, tan_fovx, tan_fovy, image_height, image_width, sh, degree, campos, prefiltered, debug)
+        return r[2:]  # (num_rendered, color, radii, geomBuffer, binningBuffer, imgBuffer)
+
+    @staticmethod
+    def count_gaussians(background, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp, viewmatrix,
+                        projmatrix, tan_fovx, tan_fovy, image_height, image_width, sh, degree, campos, prefiltered, debug, f_count=True):
+        return _forward_native(True, background, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp, viewmatrix,
+                               projmatrix, tan_fovx, tan_fovy, image_height, image_width, sh, degree, campos, prefiltered, debug)
+
+    @staticmethod
+    def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rotations, scale_modifier, cov3D_precomp, viewmatrix,
+                                     projmatrix, tan_fovx, tan_fovy, dL_dout_color, sh, degree, campos, geomBuffer, R, binningBuffer,
+                                     imageBuffer, debug):
+        lib = capi.load()
+        device = means3D.device
+        P = means3D.size(0)
+        H, W = dL_dout_color.size(1), dL_dout_color.size(2)
+        means3D_c, colors_c = _f32c(means3D, "means3D"), _f32c(colors, "colors_precomp")
+        scales_c, rot_c, cov_c, sh_c = _f32c(scales, "scales"), _f32c(rotations, "rotations"), _f32c(cov3D_precomp, "cov3D_precomp"), _f32c(sh, "sh")
+        M = 0 if sh_c is None else sh_c.size(1)
+        dpix = _f32c(dL_dout_color, "dL_dout_color")
+        mk = lambda *shape: torch.empty(shape, dtype=torch.float32, device=device)  # noqa: E731
+        dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D = mk(P, 3), mk(P, 3), mk(P, 1), mk(P, 3)
+        dL_dcov3D, dL_dsh, dL_dscales, dL_drot = mk(P, 6), mk(P, M, 3), mk(P, 3), mk(P, 4)
+        if P != 0:
+            with torch.cuda.device(device):
+                view, keep = _make_view(device, background, viewmatrix, projmatrix, campos, tan_fovx, tan_fovy, H, W, scale_modifier,
+                                        degree, False, debug)
+                st = lib.lgr_backward(C.byref(view), P, M, int(R), capi.ptr(means3D_c), capi.ptr(sh_c), capi.ptr(colors_c),
+                                      capi.ptr(scales_c), capi.ptr(rot_c), capi.ptr(cov_c), capi.ptr(radii.contiguous()),
+                                      geomBuffer.data_ptr(), binningBuffer.data_ptr(), imageBuffer.data_ptr(), dpix.data_ptr(),
+                                      dL_dmeans2D.data_ptr(), dL_dcolors.data_ptr(), dL_dopacity.data_ptr(), dL_dmeans3D.data_ptr(),
+                                      dL_dcov3D.data_ptr(), capi.ptr(dL_dsh), dL_dscales.data_ptr(), dL_drot.data_ptr(),
+                                      capi.current_stream_ptr(device))
+            capi.check(st, "lgr_backward")
+        return dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drot
+
+    @staticmethod
+    def mark_visible(means3D, viewmatrix, projmatrix):
+        lib = capi.load()
+        P = means3D.size(0)
+        present = torch.zeros((P,), dtype=torch.bool, device=means3D.device)
+        if P != 0:
+            m, v, p = _f32c(means3D, "means3D"), _f32c(viewmatrix, "viewmatrix"), _f32c(projmatrix, "projmatrix")
+            with torch.cuda.device(means3D.device):
+                st = lib.lgr_mark_visible(P, m.data_ptr(), v.data_ptr(), p.data_ptr(), present.data_ptr(),
+                                          capi.current_stream_ptr(means3D.device))
+            capi.check(st, "lgr_mark_visible")
+        return present
+
+
+_C = _NativeModule()
+
+
+def _pack_args(rs, means3D, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, sh):
+    return (rs.bg, means3D, colors_precomp, opacities, scales, rotations, rs.scale_modifier, cov3Ds_precomp, rs.viewmatrix,
+            rs.projmatrix, rs.tanfovx, rs.tanfovy, rs.image_height, rs.image_width, sh, rs.sh_degree, rs.campos, rs.prefiltered,
+            rs.debug)
+
+
+class _RasterizeGaussians(torch.autograd.Function):
+    """autograd node of the non-count path (RAST/diff_gaussian_rasterization/__init__.py:62-137,192-246)."""
+
+    @staticmethod
+    def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, raster_settings):
+        args = _pack_args(raster_settings, means3D, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, sh)
+        num_rendered, color, radii, geomBuffer, binningBuffer, imgBuffer = _C.rasterize_gaussians(*args)
+        ctx.raster_settings = raster_settings
+        ctx.num_rendered = num_rendered
+        ctx.save_for_backward(colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, geomBuffer, binningBuffer, imgBuffer)
+        ctx.mark_non_differentiable(radii)
+        return color, radii
+
+    @staticmethod
+    def backward(ctx, grad_out_color, _):
+        rs = ctx.raster_settings
+        colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, geomBuffer, binningBuffer, imgBuffer = ctx.saved_tensors
+        (grad_means2D, grad_colors_precomp, grad_opacities, grad_means3D, grad_cov3Ds_precomp, grad_sh, grad_scales,
+         grad_rotations) = _C.rasterize_gaussians_backward(
+            rs.bg, means3D, radii, colors_precomp, scales, rotations, rs.scale_modifier, cov3Ds_precomp, rs.viewmatrix, rs.projmatrix,
+            rs.tanfovx, rs.tanfovy, grad_out_color, sh, rs.sh_degree, rs.campos, geomBuffer, ctx.num_rendered, binningBuffer, imgBuffer,
+            rs.debug)
+        # gradients of absent inputs (empty tensors) must have the inputs' (empty) shape
+        def fit(g, ref):
+            return g if ref.numel() != 0 else None
+        return (grad_means3D, grad_means2D, fit(grad_sh, sh), fit(grad_colors_precomp, colors_precomp), grad_opacities,
+                fit(grad_scales, scales), fit(grad_rotations, rotations), fit(grad_cov3Ds_precomp, cov3Ds_precomp), None)
+
+    @staticmethod
+    def forward_count(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, raster_settings):
+        """No autograd, exactly like the reference (:140-189)."""
+        assert raster_settings.f_count
+        args = _pack_args(raster_settings, means3D, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, sh)
+        gaussians_count, important_score, _, color, radii, _, _, _ = _C.count_gaussians(*args, raster_settings.f_count)
+        return gaussians_count, important_score, color, radii
+
+
+def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, raster_settings):
+    if raster_settings.f_count:
+        return _RasterizeGaussians.forward_count(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                                                 raster_settings)
+    return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, raster_settings)
+
+
+class GaussianRasterizer(nn.Module):
+    def __init__(self, raster_settings):
+        super().__init__()
+        self.raster_settings = raster_settings
+
+    def markVisible(self, positions):
+        with torch.no_grad():
+            rs = self.raster_settings
+            return _C.mark_visible(positions, rs.viewmatrix, rs.projmatrix)
+
+    def _run(self, means3D, means2D, opacities, shs, colors_precomp, scales, rotations, cov3D_precomp):
+        if (shs is None) == (colors_precomp is None):
+            raise Exception("Please provide excatly one of either SHs or precomputed colors!")
+        has_sr = scales is not None or rotations is not None
+        if ((scales is None or rotations is None) and cov3D_precomp is None) or (has_sr and cov3D_precomp is not None):
+            raise Exception("Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!")
+        absent = torch.Tensor([])
+        shs = absent if shs is None else shs
+        colors_precomp = absent if colors_precomp is None else colors_precomp
+        scales = absent if scales is None else scales
+        rotations = absent if rotations is None else rotations
+        cov3D_precomp = absent if cov3D_precomp is None else cov3D_precomp
+        return rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp,
+                                   self.raster_settings)
+
+    def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None, cov3D_precomp=None):
+        return self._run(means3D, means2D, opacities, shs, colors_precomp, scales, rotations, cov3D_precomp)
+
+    def forward_count(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
+                      cov3D_precomp=None):
+        return self._run(means3D, means2D, opacities, shs, colors_precomp, scales, rotations, cov3D_precomp)

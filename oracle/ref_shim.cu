@@ -129,4 +129,7 @@ void ref_binning_ptrs(void* state, void** out)
     out[0] = bs.point_list;
 }
 
+// Device -> host copy of `n` bytes (synchronous), so Python can read the intermediates above.
+int ref_read(void* host_dst, const void* dev_src, size_t n) { return (int)cudaMemcpy(host_dst, dev_src, n, cudaMemcpyDeviceToHost); }
+
 }  // extern "C"
