@@ -197,7 +197,18 @@ def main():
     cams = [TorchCamera(c, dev) for c in cams_np]
     bg = torch.zeros(3, device=dev)
     pipe = pipeline_params()
-    flat = parallel.FlatGrads(pc.parameters())
+    params = pc.parameters()
+    grad_bytes = sum(p.numel() for p in params) * 4
+
+    def zero_grads():  # optimizer.zero_grad(set_to_none=True), as the reference loop does (prune_finetune.py:287-289)
+        for p in params:
+            p.grad = None
+
+    def allreduce_grads():  # the path's one exchange step: sum of the per-Gaussian gradients over the ranks (NCCL)
+        if world > 1:
+            hs = [torch.distributed.all_reduce(p.grad, op=torch.distributed.ReduceOp.SUM, async_op=True) for p in params]
+            for h in hs:
+                h.wait()
 
     gen = torch.Generator().manual_seed(1234)
     targets_host = [torch.rand(3, H, W, generator=gen).pin_memory() for _ in range(min(args.cams, 8))]
@@ -221,9 +232,9 @@ def main():
 
     def step_resident(step):
         i = view_index(step)
-        flat.zero()
+        zero_grads()
         loss = train_view(render_fn, cams[i], pc, pipe, bg, targets_dev[i % len(targets_dev)])
-        flat.allreduce(world)
+        allreduce_grads()
         return loss
 
     def step_e2e(step):
@@ -234,9 +245,9 @@ def main():
         cam.full_proj_transform.copy_(fp, non_blocking=True)
         cam.camera_center.copy_(cc, non_blocking=True)
         tgt = targets_host[i % len(targets_host)].to(dev, non_blocking=True)  # H2D: this step's target image
-        flat.zero()
+        zero_grads()
         loss = train_view(render_fn, cam, pc, pipe, bg, tgt)
-        flat.allreduce(world)
+        allreduce_grads()
         return float(loss.item())                                   # D2H: the step's result
 
     def barrier():
@@ -305,7 +316,7 @@ def main():
         vis, Rs = [], []
         for s in range(nprof):
             i = view_index(args.warmup + s)
-            flat.zero()
+            zero_grads()
             pkg = render_fn(cams[i], pc, pipe, bg)
             (pkg["render"] - targets_dev[i % len(targets_dev)]).abs().mean().backward()
             vis.append(int((pkg["radii"] > 0).sum().item()))
@@ -359,7 +370,8 @@ def main():
                                    "step = render()+L1+backward to raw leaves" + (" + 1 NCCL all-reduce of gradients" if world > 1 else ""),
                        "gaussians": P, "resolution": [W, H], "views_per_step": world, "parallelism": f"view-parallel x{world}",
                        "l2_policy": "inputs larger than L2 (>=0.7 GB of parameters streamed per step)",
-                       "grad_allreduce_bytes": flat.nbytes if world > 1 else 0},
+                       "grad_allreduce_bytes": grad_bytes if world > 1 else 0,
+                       "fused_activations": bool(args.impl == "ours" and os.environ.get("LGR_FUSED", "1") != "0")},
             "clocks": clocks, "gpu_launches": launches,
         }
         if args.impl == "reference":

@@ -97,6 +97,41 @@ int lgr_backward(const lgr_view* view, int P, int M, int num_rendered,
                  float* dL_dmeans2D, float* dL_dcolors, float* dL_dopacity, float* dL_dmeans3D,
                  float* dL_dcov3D, float* dL_dsh, float* dL_dscales, float* dL_drotations, void* cuda_stream);
 
+/* ---- fused-activation variants (used inside gaussian_renderer.render()) ----
+ * The six parameter leaves of GaussianModel (scene/gaussian_model.py:46-56) are read directly and the activations of
+ * its getters (:98-118: exp, normalize, sigmoid, cat) are applied in-kernel, bit-identically to the torch CUDA ops, so
+ * the result equals lgr_forward on the activated tensors.  M counts ALL SH coefficients per channel
+ * (features_dc holds 1, features_rest M-1).  features_* and rotation must be 16-byte aligned. */
+typedef struct lgr_raw_params {
+    const float* xyz;           /* [P,3]      */
+    const float* features_dc;   /* [P,1,3]    */
+    const float* features_rest; /* [P,M-1,3]  */
+    const float* scaling;       /* [P,3] log-scale         -> exp        */
+    const float* rotation;      /* [P,4] raw quaternion    -> normalize  */
+    const float* opacity;       /* [P,1] logit             -> sigmoid    */
+} lgr_raw_params;
+
+typedef struct lgr_raw_grads { /* dL/d(leaf), same shapes, fully written */
+    float* xyz;
+    float* features_dc;
+    float* features_rest;
+    float* scaling;
+    float* rotation;
+    float* opacity;
+} lgr_raw_grads;
+
+/* gaussians_count / important_score may both be NULL (plain forward) or both non-NULL (significance mode). */
+int lgr_forward_raw(const lgr_view* view, int P, int M, const lgr_raw_params* params,
+                    lgr_alloc_fn geometry_alloc, void* geometry_user,
+                    lgr_alloc_fn binning_alloc, void* binning_user,
+                    lgr_alloc_fn image_alloc, void* image_user,
+                    float* out_color, int32_t* gaussians_count, float* important_score, int32_t* radii,
+                    int32_t* num_rendered, void* cuda_stream);
+
+int lgr_backward_raw(const lgr_view* view, int P, int M, int num_rendered, const lgr_raw_params* params,
+                     const int32_t* radii, char* geometry_blob, char* binning_blob, char* image_blob,
+                     const float* dL_dout_color, const lgr_raw_grads* grads, float* dL_dmeans2D, void* cuda_stream);
+
 /* present[i] = (view-space z of point i) > 0.2   (RAST/cuda_rasterizer/rasterizer_impl.cu:54-66, auxiliary.h:139-164) */
 int lgr_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix, uint8_t* present,
                      void* cuda_stream);

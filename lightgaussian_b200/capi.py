@@ -27,6 +27,12 @@ class LgrView(C.Structure):
     ]
 
 
+class LgrRawParams(C.Structure):
+    """struct lgr_raw_params / lgr_raw_grads (same layout: six pointers)"""
+    _fields_ = [("xyz", C.c_void_p), ("features_dc", C.c_void_p), ("features_rest", C.c_void_p), ("scaling", C.c_void_p),
+                ("rotation", C.c_void_p), ("opacity", C.c_void_p)]
+
+
 ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t)
 
 _lib = None
@@ -59,6 +65,12 @@ def load():
         lib.lgr_forward_count.argtypes = fwd_common + [vp, vp, vp, vp, C.POINTER(C.c_int32), vp]
         lib.lgr_backward.restype = i32
         lib.lgr_backward.argtypes = [C.POINTER(LgrView), i32, i32, i32] + [vp] * 20
+        lib.lgr_forward_raw.restype = i32
+        lib.lgr_forward_raw.argtypes = [C.POINTER(LgrView), i32, i32, C.POINTER(LgrRawParams), ALLOC_FN, vp, ALLOC_FN, vp, ALLOC_FN, vp,
+                                        vp, vp, vp, vp, C.POINTER(C.c_int32), vp]
+        lib.lgr_backward_raw.restype = i32
+        lib.lgr_backward_raw.argtypes = [C.POINTER(LgrView), i32, i32, i32, C.POINTER(LgrRawParams), vp, vp, vp, vp, vp,
+                                         C.POINTER(LgrRawParams), vp, vp]
         lib.lgr_mark_visible.restype = i32
         lib.lgr_mark_visible.argtypes = [i32, vp, vp, vp, vp, vp]
         lib.lgr_last_error.restype = C.c_char_p

@@ -634,8 +634,13 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
             float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f, v4 = 0.f, v5 = 0.f, v6 = 0.f, v7 = 0.f, v8 = 0.f;
             if (on) {
                 const float4 f = s_rgb[warp][j];
+                // 1/(1-alpha): 1-alpha is in [0.01, 0.996], so MUFU.RCP + one Newton step is within 1 ulp and needs no
+                // range fix-up (the two IEEE divisions of the reference cost ~25 instructions here)
                 const float one_m_a = 1.0f - alpha;
-                T = T / one_m_a;
+                float rcp;
+                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rcp) : "f"(one_m_a));
+                rcp = fmaf(rcp, fmaf(-one_m_a, rcp, 1.0f), rcp);
+                T = T * rcp;
                 const float w = alpha * T;
                 a0 = last_alpha * lc0 + (1.f - last_alpha) * a0;
                 a1 = last_alpha * lc1 + (1.f - last_alpha) * a1;
@@ -645,7 +650,7 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
                 v0 = w * d0; v1 = w * d1; v2 = w * d2;
                 dL_dalpha *= T;
                 last_alpha = alpha;
-                dL_dalpha += (-T_final / one_m_a) * bg_dot;
+                dL_dalpha += (-T_final * rcp) * bg_dot;
                 const float dL_dG = c.w * dL_dalpha;
                 const float gdx = G * dx, gdy = G * dy;
                 const float dG_ddelx = -gdx * c.x - gdy * c.y;
@@ -783,6 +788,10 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(PreBackArgs a)
     }
 }
 
+}  // namespace
+#include "lgr_raw.cuh"
+namespace {
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -801,9 +810,24 @@ int forward_impl(const lgr_view* v, int P, int M, const float* means3D, const fl
                  const float* opacities, const float* scales, const float* rotations, const float* cov3D_precomp,
                  lgr_alloc_fn geometry_alloc, void* geometry_user, lgr_alloc_fn binning_alloc, void* binning_user,
                  lgr_alloc_fn image_alloc, void* image_user, float* out_color, int32_t* gaussians_count, float* important_score,
-                 int32_t* radii, int32_t* num_rendered, void* cuda_stream, bool count_mode)
+                 int32_t* radii, int32_t* num_rendered, void* cuda_stream, bool count_mode, const lgr_raw_params* raw = nullptr)
 {
     cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+    if (raw) {  // fused-activation path: the six leaves replace the activated tensors
+        means3D = raw->xyz;
+        opacities = raw->opacity;
+        scales = raw->scaling;
+        rotations = raw->rotation;
+        shs = raw->features_dc;
+        if (P > 0 && (!raw->xyz || !raw->opacity || !raw->scaling || !raw->rotation || !raw->features_dc || (M > 1 && !raw->features_rest))) {
+            g_last_error = "lgr_forward_raw: a parameter leaf is NULL";
+            return LGR_ERR_INVALID_ARG;
+        }
+        if (((uintptr_t)raw->features_rest & 15) || ((uintptr_t)raw->features_dc & 15)) {
+            g_last_error = "lgr_forward_raw: features_dc / features_rest must be 16-byte aligned";
+            return LGR_ERR_INVALID_ARG;
+        }
+    }
     if (!v || P < 0 || M < 0 || !num_rendered || !out_color || !geometry_alloc || !binning_alloc || !image_alloc) {
         g_last_error = "lgr_forward: missing required argument";
         return LGR_ERR_INVALID_ARG;
@@ -863,7 +887,18 @@ int forward_impl(const lgr_view* v, int P, int M, const float* means3D, const fl
         a.cov3D_precomp = cov3D_precomp; a.colors_precomp = colors_precomp;
         a.view = v->viewmatrix; a.proj = v->projmatrix; a.campos = v->campos; a.prefiltered = v->prefiltered;
         const int blocks = (P + 255) / 256;
-        {
+        if (raw) {
+            RawArgs ra;
+            ra.P = P; ra.D = a.D; ra.M = M; ra.W = W; ra.H = H; ra.gx = gx; ra.gy = gy;
+            ra.fx = a.fx; ra.fy = a.fy; ra.tanx = a.tanx; ra.tany = a.tany; ra.mod = a.mod;
+            ra.xyz = raw->xyz; ra.dc = raw->features_dc; ra.rest = raw->features_rest; ra.scaling = raw->scaling;
+            ra.rotation = raw->rotation; ra.opacity = raw->opacity; ra.view = a.view; ra.proj = a.proj; ra.campos = a.campos;
+            ra.prefiltered = a.prefiltered;
+            const size_t smem = raw_smem_bytes(M);
+            LGR_CUDA_TRY(cudaFuncSetAttribute(preprocess_raw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ProfScope ps(ST_PREPROCESS, stream);
+            preprocess_raw_kernel<<<blocks, 256, smem, stream>>>(ra, radii, geo);
+        } else {
             ProfScope ps(ST_PREPROCESS, stream);
             preprocess_kernel<<<blocks, 256, 0, stream>>>(a, radii, geo);
         }
@@ -944,7 +979,8 @@ int forward_impl(const lgr_view* v, int P, int M, const float* means3D, const fl
     }
     if (count_mode && P > 0) {
         ProfScope ps(ST_SCORE, stream);
-        score_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, gaussians_count, opacities, important_score);
+        if (raw) score_from_geom_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, gaussians_count, geo.conic_opacity, important_score);
+        else score_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, gaussians_count, opacities, important_score);
         LGR_LAUNCH_CHECK("score_kernel", debug, stream);
     }
     (void)N;
@@ -1086,6 +1122,74 @@ int lgr_backward(const lgr_view* v, int P, int M, int num_rendered, const float*
         preprocess_backward_kernel<<<(P + 255) / 256, 256, 0, stream>>>(a);
     }
     LGR_LAUNCH_CHECK("preprocess_backward_kernel", debug, stream);
+    return LGR_OK;
+}
+
+int lgr_forward_raw(const lgr_view* view, int P, int M, const lgr_raw_params* params, lgr_alloc_fn geometry_alloc, void* geometry_user,
+                    lgr_alloc_fn binning_alloc, void* binning_user, lgr_alloc_fn image_alloc, void* image_user, float* out_color,
+                    int32_t* gaussians_count, float* important_score, int32_t* radii, int32_t* num_rendered, void* cuda_stream)
+{
+    if (!params || M < 1) {
+        g_last_error = "lgr_forward_raw: params missing or M < 1";
+        return LGR_ERR_INVALID_ARG;
+    }
+    const bool count_mode = gaussians_count != nullptr;
+    return forward_impl(view, P, M, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, geometry_alloc, geometry_user,
+                        binning_alloc, binning_user, image_alloc, image_user, out_color, gaussians_count, important_score, radii,
+                        num_rendered, cuda_stream, count_mode, params);
+}
+
+int lgr_backward_raw(const lgr_view* v, int P, int M, int num_rendered, const lgr_raw_params* params, const int32_t* radii,
+                     char* geometry_blob, char* binning_blob, char* image_blob, const float* dL_dout_color, const lgr_raw_grads* grads,
+                     float* dL_dmeans2D, void* cuda_stream)
+{
+    cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+    if (P == 0) return LGR_OK;
+    if (!v || P < 0 || M < 1 || !params || !grads || !radii || !geometry_blob || !binning_blob || !image_blob || !dL_dout_color ||
+        !dL_dmeans2D || !grads->xyz || !grads->features_dc || (M > 1 && !grads->features_rest) || !grads->scaling || !grads->rotation ||
+        !grads->opacity) {
+        g_last_error = "lgr_backward_raw: missing required argument";
+        return LGR_ERR_INVALID_ARG;
+    }
+    if (((uintptr_t)params->rotation & 15) || ((uintptr_t)grads->rotation & 15) || ((uintptr_t)params->features_rest & 15) ||
+        ((uintptr_t)params->features_dc & 15) || ((uintptr_t)grads->features_rest & 15) || ((uintptr_t)grads->features_dc & 15)) {
+        g_last_error = "lgr_backward_raw: rotation / features tensors and their gradients must be 16-byte aligned";
+        return LGR_ERR_INVALID_ARG;
+    }
+    const bool debug = v->debug != 0;
+    const int W = v->image_width, H = v->image_height;
+    const int gx = (W + LGR_TILE - 1) / LGR_TILE, gy = (H + LGR_TILE - 1) / LGR_TILE;
+    GeometryState geo = carve_geometry(geometry_blob, (size_t)P);
+    ImageState img = carve_image(image_blob, W, H);
+    BinningState bin = carve_binning(binning_blob, (size_t)(num_rendered > 0 ? num_rendered : 0), W, H);
+    {
+        ProfScope ps(ST_MEMSET, stream);
+        LGR_CUDA_TRY(cudaMemsetAsync(geo.grad_acc, 0, sizeof(float) * ACC_STRIDE * (size_t)P, stream));
+    }
+    if (num_rendered > 0) {
+        ProfScope ps(ST_BLEND_BWD, stream);
+        blend_backward_kernel<<<gx * gy, 256, 0, stream>>>(img.ranges, bin.point_list, W, H, gx, geo.means2D, geo.conic_opacity, geo.rgb,
+                                                            v->background, img.final_T, img.n_contrib, dL_dout_color, geo.grad_acc);
+        LGR_LAUNCH_CHECK("blend_backward_kernel", debug, stream);
+    }
+    RawBackArgs a;
+    a.P = P; a.D = v->sh_degree; a.M = M; a.W = W; a.H = H;
+    a.fy = H / (2.0f * v->tan_fovy);
+    a.fx = W / (2.0f * v->tan_fovx);
+    a.tanx = v->tan_fovx; a.tany = v->tan_fovy; a.mod = v->scale_modifier;
+    a.xyz = params->xyz; a.dc = params->features_dc; a.rest = params->features_rest; a.scaling = params->scaling;
+    a.rotation = params->rotation; a.cov3D = geo.cov3D; a.conic_opacity = geo.conic_opacity;
+    a.view = v->viewmatrix; a.proj = v->projmatrix; a.campos = v->campos;
+    a.radii = radii; a.clamped = geo.clamped; a.acc = geo.grad_acc;
+    a.d_xyz = grads->xyz; a.d_dc = grads->features_dc; a.d_rest = grads->features_rest; a.d_scaling = grads->scaling;
+    a.d_rotation = grads->rotation; a.d_opacity = grads->opacity; a.dL_dmeans2D = dL_dmeans2D;
+    const size_t smem = raw_smem_bytes(M);
+    LGR_CUDA_TRY(cudaFuncSetAttribute(preprocess_backward_raw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {
+        ProfScope ps(ST_PREPROCESS_BWD, stream);
+        preprocess_backward_raw_kernel<<<(P + 255) / 256, 256, smem, stream>>>(a);
+    }
+    LGR_LAUNCH_CHECK("preprocess_backward_raw_kernel", debug, stream);
     return LGR_OK;
 }
 

@@ -256,3 +256,119 @@ class GaussianRasterizer(nn.Module):
     def forward_count(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
                       cov3D_precomp=None):
         return self._run(means3D, means2D, opacities, shs, colors_precomp, scales, rotations, cov3D_precomp)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Fused-activation path: the rasterizer consumes GaussianModel's six raw leaves.
+# Only gaussian_renderer.render()/count_render() use it; the reference-compatible API above is unchanged.
+# ------------------------------------------------------------------------------------------------------------------
+def _raw_struct(xyz, dc, rest, scaling, rotation, opacity):
+    return capi.LgrRawParams(capi.ptr(xyz), capi.ptr(dc), capi.ptr(rest), capi.ptr(scaling), capi.ptr(rotation), capi.ptr(opacity))
+
+
+def _forward_raw_native(count_mode, rs, xyz, dc, rest, scaling, rotation, opacity):
+    lib = capi.load()
+    device = xyz.device
+    P, H, W = xyz.size(0), int(rs.image_height), int(rs.image_width)
+    M = 1 + rest.size(1)
+    leaves = [_f32c(t, n) if t.numel() else t for t, n in
+              ((xyz, "xyz"), (dc, "features_dc"), (rest, "features_rest"), (scaling, "scaling"), (rotation, "rotation"), (opacity, "opacity"))]
+    out_color = torch.empty((3, H, W), dtype=torch.float32, device=device)
+    radii = torch.empty((P,), dtype=torch.int32, device=device)
+    count = score = None
+    if count_mode:
+        count = torch.empty((P,), dtype=torch.int32, device=device)
+        score = torch.empty((P,), dtype=torch.float32, device=device)
+    slots = [capi.BlobSlot(device) for _ in range(3)]
+    num_rendered = C.c_int32(0)
+    try:
+        with torch.cuda.device(device):
+            view, keep = _make_view(device, rs.bg, rs.viewmatrix, rs.projmatrix, rs.campos, rs.tanfovx, rs.tanfovy, H, W, rs.scale_modifier,
+                                    rs.sh_degree, rs.prefiltered, rs.debug)
+            params = _raw_struct(*leaves)
+            st = lib.lgr_forward_raw(C.byref(view), P, M, C.byref(params), capi.ALLOC_CB, slots[0].key, capi.ALLOC_CB, slots[1].key,
+                                     capi.ALLOC_CB, slots[2].key, out_color.data_ptr(), capi.ptr(count), capi.ptr(score), capi.ptr(radii),
+                                     C.byref(num_rendered), capi.current_stream_ptr(device))
+        capi.check(st, "lgr_forward_raw")
+    finally:
+        for s_ in slots:
+            s_.release()
+    empty = lambda: torch.empty((0,), dtype=torch.uint8, device=device)  # noqa: E731
+    geom, binning, img = (s_.tensor if s_.tensor is not None else empty() for s_ in slots)
+    _last_R[0] = int(num_rendered.value)
+    if P == 0:
+        radii = torch.zeros((0,), dtype=torch.int32, device=device)
+    return count, score, int(num_rendered.value), out_color, radii, geom, binning, img, leaves
+
+
+class _RasterizeRawLeaves(torch.autograd.Function):
+    """render()'s node when the fused path applies: inputs are the six leaves, gradients come back for the leaves."""
+
+    @staticmethod
+    def forward(ctx, xyz, means2D, dc, rest, scaling, rotation, opacity, raster_settings):
+        _, _, R, color, radii, geom, binning, img, leaves = _forward_raw_native(False, raster_settings, xyz, dc, rest, scaling, rotation, opacity)
+        ctx.raster_settings = raster_settings
+        ctx.num_rendered = R
+        ctx.save_for_backward(*leaves, radii, geom, binning, img)
+        ctx.mark_non_differentiable(radii)
+        return color, radii
+
+    @staticmethod
+    def backward(ctx, grad_out_color, _):
+        rs = ctx.raster_settings
+        xyz, dc, rest, scaling, rotation, opacity, radii, geom, binning, img = ctx.saved_tensors
+        lib = capi.load()
+        device = xyz.device
+        P, M = xyz.size(0), 1 + rest.size(1)
+        H, W = grad_out_color.size(1), grad_out_color.size(2)
+        g = [torch.empty_like(t) for t in (xyz, dc, rest, scaling, rotation, opacity)]
+        g2d = torch.empty((P, 3), dtype=torch.float32, device=device)
+        if P != 0:
+            dpix = _f32c(grad_out_color, "grad_out_color")
+            with torch.cuda.device(device):
+                view, keep = _make_view(device, rs.bg, rs.viewmatrix, rs.projmatrix, rs.campos, rs.tanfovx, rs.tanfovy, H, W,
+                                        rs.scale_modifier, rs.sh_degree, False, rs.debug)
+                params, grads = _raw_struct(xyz, dc, rest, scaling, rotation, opacity), _raw_struct(*g)
+                st = lib.lgr_backward_raw(C.byref(view), P, M, int(ctx.num_rendered), C.byref(params), radii.data_ptr(), geom.data_ptr(),
+                                          binning.data_ptr(), img.data_ptr(), dpix.data_ptr(), C.byref(grads), g2d.data_ptr(),
+                                          capi.current_stream_ptr(device))
+            capi.check(st, "lgr_backward_raw")
+        return g[0], g2d, g[1], g[2], g[3], g[4], g[5], None
+
+
+def rasterize_raw_leaves(xyz, means2D, features_dc, features_rest, scaling, rotation, opacity, raster_settings):
+    """(color, radii) or, in count mode, (gaussians_count, important_score, color, radii) -- same as rasterize_gaussians."""
+    if raster_settings.f_count:
+        count, score, _, color, radii, _, _, _, _ = _forward_raw_native(True, raster_settings, xyz.detach(), features_dc.detach(),
+                                                                        features_rest.detach(), scaling.detach(), rotation.detach(),
+                                                                        opacity.detach())
+        return count, score, color, radii
+    return _RasterizeRawLeaves.apply(xyz, means2D, features_dc, features_rest, scaling, rotation, opacity, raster_settings)
+
+
+_fused_ok = {}
+
+
+def fused_activations_match_torch(device) -> bool:
+    """One-time self-check per device: the in-kernel activations are only used when they reproduce this torch build's
+    exp / sigmoid / F.normalize bit for bit (otherwise render() silently keeps the unfused path)."""
+    key = str(device)
+    if key not in _fused_ok:
+        g = torch.Generator().manual_seed(1)
+        P = 4096
+        raw = dict(xyz=torch.randn(P, 3, generator=g), dc=torch.randn(P, 1, 3, generator=g), rest=torch.randn(P, 15, 3, generator=g) * 0.2,
+                   scaling=torch.randn(P, 3, generator=g) * 0.5 - 4.0, rotation=torch.randn(P, 4, generator=g), opacity=torch.randn(P, 1, generator=g) * 2)
+        raw = {k: v.to(device) for k, v in raw.items()}
+        eye = torch.eye(4, device=device)
+        view = eye.clone(); view[3, 2] = 4.0
+        proj = view.clone(); proj[2, 3] = 1.0
+        rs = GaussianRasterizationSettings(64, 64, 0.6, 0.6, torch.zeros(3, device=device), 1.0, view, proj, 3, torch.zeros(3, device=device),
+                                           False, False, False)
+        with torch.no_grad():
+            a = _forward_raw_native(False, rs, raw["xyz"], raw["dc"], raw["rest"], raw["scaling"], raw["rotation"], raw["opacity"])
+            act = (rs.bg, raw["xyz"], torch.Tensor([]), torch.sigmoid(raw["opacity"]), torch.exp(raw["scaling"]),
+                   torch.nn.functional.normalize(raw["rotation"]), 1.0, torch.Tensor([]), view, proj, 0.6, 0.6, 64, 64,
+                   torch.cat((raw["dc"], raw["rest"]), dim=1), 3, rs.campos, False, False)
+            b = _C.rasterize_gaussians(*act)
+        _fused_ok[key] = bool(torch.equal(a[3], b[1]) and torch.equal(a[4], b[2]) and a[2] == b[0])
+    return _fused_ok[key]

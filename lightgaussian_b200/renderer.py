@@ -12,7 +12,38 @@ import math
 
 import torch
 
-from .rasterizer import GaussianRasterizationSettings, GaussianRasterizer
+import os
+
+import torch.nn.functional as F
+
+from .rasterizer import (GaussianRasterizationSettings, GaussianRasterizer, rasterize_raw_leaves, fused_activations_match_torch)
+
+_LEAVES = ("_xyz", "_features_dc", "_features_rest", "_scaling", "_rotation", "_opacity")
+
+
+def _can_fuse(pc, pipe, override_color) -> bool:
+    """The fused path needs GaussianModel-style raw leaves with the standard activations
+    (scene/gaussian_model.py:35-43: exp / sigmoid / normalize) and the default pipeline flags."""
+    if os.environ.get("LGR_FUSED", "1") == "0" or override_color is not None:
+        return False
+    if pipe.convert_SHs_python or pipe.compute_cov3D_python:
+        return False
+    if not all(hasattr(pc, n) for n in _LEAVES):
+        return False
+    if getattr(pc, "scaling_activation", torch.exp) is not torch.exp:
+        return False
+    if getattr(pc, "opacity_activation", torch.sigmoid) is not torch.sigmoid:
+        return False
+    if getattr(pc, "rotation_activation", F.normalize) is not F.normalize:
+        return False
+    t = pc._xyz
+    if not (t.is_cuda and all(getattr(pc, n).dtype == torch.float32 and getattr(pc, n).is_contiguous() for n in _LEAVES)):
+        return False
+    if pc._features_rest.dim() != 3 or pc._features_dc.shape[1] != 1 or pc._features_rest.shape[1] < 1:
+        return False
+    if (pc.active_sh_degree + 1) ** 2 > 1 + pc._features_rest.shape[1]:
+        return False
+    return fused_activations_match_torch(t.device)
 
 _SH_C0 = 0.28209479177387814
 _SH_C1 = 0.4886025119029199
@@ -64,6 +95,11 @@ def _render(viewpoint_camera, pc, pipe, bg_color, scaling_modifier, override_col
         debug=pipe.debug,
         f_count=f_count,
     )
+    if _can_fuse(pc, pipe, override_color):
+        outputs = rasterize_raw_leaves(pc._xyz, screenspace_points, pc._features_dc, pc._features_rest, pc._scaling, pc._rotation,
+                                       pc._opacity, settings)
+        return _package(outputs, screenspace_points, f_count)
+
     rasterizer = GaussianRasterizer(raster_settings=settings)
 
     geometry = dict(scales=None, rotations=None, cov3D_precomp=None)
@@ -85,6 +121,10 @@ def _render(viewpoint_camera, pc, pipe, bg_color, scaling_modifier, override_col
         appearance["shs"] = pc.get_features
 
     outputs = rasterizer(means3D=xyz, means2D=screenspace_points, opacities=pc.get_opacity, **appearance, **geometry)
+    return _package(outputs, screenspace_points, f_count)
+
+
+def _package(outputs, screenspace_points, f_count):
     if f_count:
         gaussians_count, important_score, rendered_image, radii = outputs
     else:

@@ -1,0 +1,83 @@
+"""render()'s fused-activation path (raw leaves + TMA-staged SH rows) against the reference-compatible path
+(torch activations + cat -> rasterizer) of the SAME library: images / radii / counts must be bit-identical,
+leaf gradients equal up to the atomics' summation order."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from lightgaussian_b200.model import GaussianParams, TorchCamera, pipeline_params
+from lightgaussian_b200.synth import make_scene, make_cameras, inside_camera
+from tests.util import rel_inf, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def _render_both(P, W, H, deg_active, M, cam_np, seed, scale_mult=1.5, count=False):
+    from lightgaussian_b200 import renderer
+    scene = make_scene(P, sh_degree=3, seed=seed, scale_mult=scale_mult)
+    raw = dict(scene["raw"])
+    raw["features_rest"] = np.ascontiguousarray(raw["features_rest"][:, :M - 1])
+    cam = TorchCamera(cam_np, "cuda")
+    bg = torch.tensor([0.2, 0.4, 0.6], device="cuda")
+    pipe = pipeline_params()
+    tgt = torch.rand(3, H, W, generator=torch.Generator().manual_seed(3)).cuda()
+    out = {}
+    for mode in ("fused", "plain"):
+        os.environ["LGR_FUSED"] = "1" if mode == "fused" else "0"
+        pc = GaussianParams(raw, 3, "cuda")
+        pc.active_sh_degree = deg_active
+        fn = renderer.count_render if count else renderer.render
+        pkg = fn(cam, pc, pipe, bg)
+        res = {k: v.detach().cpu().numpy() for k, v in pkg.items() if k != "viewspace_points"}
+        if not count:
+            ((pkg["render"] - tgt) ** 2).mean().backward()
+            res["grads"] = [p.grad.detach().cpu().numpy() for p in pc.parameters()]
+            res["g2d"] = pkg["viewspace_points"].grad.detach().cpu().numpy()
+        out[mode] = res
+    os.environ["LGR_FUSED"] = "1"
+    return out
+
+
+def test_inkernel_activations_match_this_torch_build():
+    from lightgaussian_b200.rasterizer import fused_activations_match_torch
+    assert fused_activations_match_torch(torch.device("cuda", 0)), \
+        "exp / sigmoid / F.normalize of this torch build no longer match lgr_raw.cuh's operation order"
+
+
+@pytest.mark.parametrize("P,W,H,deg,M", [(4096, 160, 120, 3, 16), (1000 + 13, 96, 80, 3, 16), (2048 + 7, 128, 96, 2, 16),
+                                         (1500, 96, 64, 1, 16), (1200, 64, 64, 0, 16), (3000 + 5, 128, 96, 2, 9), (777, 64, 48, 1, 4)])
+def test_fused_equals_plain(P, W, H, deg, M):
+    cam = make_cameras(5, W, H)[2]
+    o = _render_both(P, W, H, deg, M, cam, seed=100 + P)
+    f, p = o["fused"], o["plain"]
+    assert (p["radii"] > 0).sum() > 20
+    np.testing.assert_array_equal(f["radii"], p["radii"])
+    np.testing.assert_array_equal(f["render"], p["render"])          # bit-identical image
+    for a, b, name in zip(f["grads"], p["grads"], ("xyz", "dc", "rest", "scaling", "rotation", "opacity")):
+        assert a.shape == b.shape and np.isfinite(a).all()
+        assert rel_inf(a, b) <= 1e-3, f"{name}: {rel_inf(a, b)}"
+        assert rel_l2(a, b) <= 1e-4, f"{name}: {rel_l2(a, b)}"
+    assert rel_inf(f["g2d"], p["g2d"]) <= 1e-3
+
+
+def test_fused_equals_plain_with_heavy_culling():
+    W, H = 160, 112
+    o = _render_both(5000, W, H, 3, 16, inside_camera(W, H), seed=9, scale_mult=1.0)
+    f, p = o["fused"], o["plain"]
+    assert 0 < (p["radii"] > 0).sum() < 2500
+    np.testing.assert_array_equal(f["render"], p["render"])
+    for a, b in zip(f["grads"], p["grads"]):
+        assert rel_inf(a, b) <= 1e-3
+        assert np.all(a[p["radii"] <= 0] == 0)
+
+
+def test_fused_count_render_equals_plain():
+    W, H = 128, 96
+    o = _render_both(3000 + 11, W, H, 3, 16, make_cameras(5, W, H)[1], seed=4, count=True)
+    f, p = o["fused"], o["plain"]
+    np.testing.assert_array_equal(f["render"], p["render"])
+    np.testing.assert_array_equal(f["gaussians_count"], p["gaussians_count"])
+    np.testing.assert_array_equal(f["important_score"], p["important_score"])
+    assert f["gaussians_count"].sum() > 0
