@@ -251,17 +251,17 @@ __global__ void __launch_bounds__(256) preprocess_backward_raw_kernel(RawBackArg
     float dop = 0.f, g2x = 0.f, g2y = 0.f, dRGB[3] = {0.f, 0.f, 0.f};
     float x = 0.f, y = 0.f, z = 0.f;
     if (vis) {
-        const float4* rec4 = reinterpret_cast<const float4*>(a.acc + si * ACC_STRIDE);
-        const float4 r0 = rec4[0], r1 = rec4[1], r2 = rec4[2];
+        const float4 co = a.conic_opacity[si];
+        const Grad2D g2 = accum_to_grad2d(a.acc + si * ACC_STRIDE, co, a.W, a.H);
         x = a.xyz[3 * si]; y = a.xyz[3 * si + 1]; z = a.xyz[3 * si + 2];
         float c3[6], dcov[6];
 #pragma unroll
         for (int k = 0; k < 6; k++) c3[k] = a.cov3D[6 * si + k];
-        lgr::cov2d_backward(x, y, z, view, c3, a.fx, a.fy, a.tanx, a.tany, r1.z, r1.w, r2.x, dcov, dmean);
-        lgr::mean2d_backward(x, y, z, proj, r1.x, r1.y, dmean);
-        g2x = r1.x; g2y = r1.y;
+        lgr::cov2d_backward(x, y, z, view, c3, a.fx, a.fy, a.tanx, a.tany, g2.dcx, g2.dcy, g2.dcw, dcov, dmean);
+        lgr::mean2d_backward(x, y, z, proj, g2.dm2x, g2.dm2y, dmean);
+        g2x = g2.dm2x; g2y = g2.dm2y;
         const unsigned cb = a.clamped[i];
-        dRGB[0] = (cb & 1u) ? 0.f : r0.x; dRGB[1] = (cb & 2u) ? 0.f : r0.y; dRGB[2] = (cb & 4u) ? 0.f : r0.z;
+        dRGB[0] = (cb & 1u) ? 0.f : g2.dcol[0]; dRGB[1] = (cb & 2u) ? 0.f : g2.dcol[1]; dRGB[2] = (cb & 4u) ? 0.f : g2.dcol[2];
         // scale / rotation chain: activations recomputed, then d/d(raw)
         const float s0 = act_exp(a.scaling[3 * si]), s1 = act_exp(a.scaling[3 * si + 1]), s2 = act_exp(a.scaling[3 * si + 2]);
         float dn;
@@ -275,8 +275,8 @@ __global__ void __launch_bounds__(256) preprocess_backward_raw_kernel(RawBackArg
         const float inv = 1.0f / dn;
         dq[0] = (dqn[0] - q.x * qg) * inv; dq[1] = (dqn[1] - q.y * qg) * inv;
         dq[2] = (dqn[2] - q.z * qg) * inv; dq[3] = (dqn[3] - q.w * qg) * inv;
-        const float o = a.conic_opacity[si].w;  // sigmoid(raw), stored by the forward
-        dop = (r0.w * (1.0f - o)) * o;          // sigmoid_backward: grad * (1 - y) * y
+        const float o = co.w;                    // sigmoid(raw), stored by the forward
+        dop = (g2.dop * (1.0f - o)) * o;         // sigmoid_backward: grad * (1 - y) * y
     }
     if (need_sh) {
         if (bulk) mbar_wait(&bars[warp], 0);

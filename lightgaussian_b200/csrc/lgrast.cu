@@ -34,7 +34,9 @@ namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int ACC_STRIDE = 12;  // floats per Gaussian in the backward accumulator record
-// record layout: 0..2 dL/dcolor rgb | 3 dL/dopacity | 4,5 dL/dmean2D xy | 6,7,8 dL/dconic x,y,w | 9..11 pad
+// record layout: 0..2 dL/dcolor rgb | 3 S0 | 4,5 S1x,S1y | 6,7,8 S2xx,S2xy,S2yy | 9..11 pad
+// with w = G * dL/dalpha per (pixel, Gaussian) pair and d = mean2D - pixel:  S0 = sum w, S1 = sum w*d, S2 = sum w*d*d^T.
+// The per-Gaussian factors (conic, opacity, viewport) are applied once per Gaussian in K8 (accum_to_grad2d).
 
 thread_local std::string g_last_error;
 std::atomic<uint64_t> g_launches{0};
@@ -333,43 +335,81 @@ __global__ void __launch_bounds__(256) preprocess_kernel(PreprocessArgs a, int* 
 // ------------------------------------------------------------------------------------------------
 // K2  emit (tile, id) instances in depth order     (RAST/cuda_rasterizer/rasterizer_impl.cu:70-111)
 // ------------------------------------------------------------------------------------------------
+// Warp-cooperative: the 32 Gaussians of a warp own one contiguous span of the instance list; lane L writes
+// instances span_begin+L, +32, ... and finds each instance's owner with a 5-step shuffle binary search over the
+// warp's run offsets, so key/id stores are fully coalesced whatever the splat sizes are (the reference's one thread
+// per Gaussian loop is serial in the splat area, rasterizer_impl.cu:98-109).
 template <typename KeyT>
 __global__ void __launch_bounds__(256) emit_kernel(int P, const uint32_t* __restrict__ sorted_ids, const uint32_t* __restrict__ offsets,
                                                    const uint32_t* __restrict__ tiles_touched, const float2* __restrict__ means2D,
                                                    const int* __restrict__ radii, int gx, int gy, KeyT* __restrict__ keys,
                                                    uint32_t* __restrict__ ids)
 {
+    const int lane = threadIdx.x & 31;
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= P) return;
-    const uint32_t id = sorted_ids[k];
-    if (tiles_touched[id] == 0) return;
-    uint32_t off = (k == 0) ? 0u : offsets[k - 1];
-    const float2 p = means2D[id];
-    const lgr::TileRect r = lgr::tile_rect(p.x, p.y, radii[id], gx, gy);
-    for (int ty = r.y0; ty < r.y1; ty++)
-        for (int tx = r.x0; tx < r.x1; tx++) {
-            keys[off] = (KeyT)(ty * gx + tx);
-            ids[off] = id;
-            off++;
-        }
-}
-
-// K3  per-tile ranges from the sorted tile keys    (RAST/cuda_rasterizer/rasterizer_impl.cu:116-138)
-template <typename KeyT>
-__global__ void __launch_bounds__(256) ranges_kernel(int R, const KeyT* __restrict__ keys, uint2* __restrict__ ranges)
-{
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= R) return;
-    const uint32_t t = keys[k];
-    if (k == 0) ranges[t].x = 0;
-    else {
-        const uint32_t prev = keys[k - 1];
-        if (prev != t) {
-            ranges[prev].y = k;
-            ranges[t].x = k;
+    uint32_t id = 0, cnt = 0, off = 0;
+    int x0 = 0, y0 = 0, w = 1;
+    if (k < P) {
+        id = sorted_ids[k];
+        cnt = tiles_touched[id];
+        off = offsets[k] - cnt;  // offsets = inclusive scan in sorted order
+        if (cnt) {
+            const float2 p = means2D[id];
+            const lgr::TileRect r = lgr::tile_rect(p.x, p.y, radii[id], gx, gy);
+            x0 = r.x0; y0 = r.y0; w = r.x1 - r.x0;
         }
     }
-    if (k == R - 1) ranges[t].y = R;
+    // lanes past P inherit the running offset so that `off` stays non-decreasing across the warp
+    const uint32_t end_mine = off + cnt;
+    uint32_t run_end = end_mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(FULL, run_end, d);
+        if (lane >= d) run_end = max(run_end, t);
+    }
+    if (k >= P) off = run_end;
+    const uint32_t span_begin = __shfl_sync(FULL, off, 0);
+    const uint32_t span_end = __shfl_sync(FULL, run_end, 31);
+    for (uint32_t base = span_begin; base < span_end; base += 32) {
+        const uint32_t j = base + lane;
+        int lo = 0, hi = 31;  // largest lane m with off[m] <= j
+#pragma unroll
+        for (int it = 0; it < 5; it++) {
+            const int mid = (lo + hi + 1) >> 1;
+            const uint32_t v = __shfl_sync(FULL, off, mid);
+            if (v <= j) lo = mid;
+            else hi = mid - 1;
+        }
+        const uint32_t o_off = __shfl_sync(FULL, off, lo);
+        const uint32_t o_id = __shfl_sync(FULL, id, lo);
+        const int o_x0 = __shfl_sync(FULL, x0, lo), o_y0 = __shfl_sync(FULL, y0, lo), o_w = __shfl_sync(FULL, w, lo);
+        if (j < span_end) {
+            const int local = (int)(j - o_off);
+            const int ry = local / o_w, rx = local - ry * o_w;
+            keys[j] = (KeyT)((o_y0 + ry) * gx + (o_x0 + rx));
+            ids[j] = o_id;
+        }
+    }
+}
+
+// K3  per-tile ranges: two binary searches per tile in the sorted tile keys (the reference scans all R keys,
+// RAST/cuda_rasterizer/rasterizer_impl.cu:116-138).  Empty tiles get (0,0) like the reference's memset.
+template <typename KeyT>
+__global__ void __launch_bounds__(256) ranges_kernel(int R, int tiles, const KeyT* __restrict__ keys, uint2* __restrict__ ranges)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= tiles) return;
+    auto lower = [&](uint32_t key) {
+        int lo = 0, hi = R;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if ((uint32_t)keys[mid] < key) lo = mid + 1;
+            else hi = mid;
+        }
+        return (uint32_t)lo;
+    };
+    const uint32_t a = lower((uint32_t)t), b = lower((uint32_t)t + 1u);
+    ranges[t] = (b > a) ? make_uint2(a, b) : make_uint2(0u, 0u);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -513,50 +553,28 @@ __global__ void __launch_bounds__(256) mark_visible_kernel(int P, const float* _
 
 // ------------------------------------------------------------------------------------------------
 // K6  backward blend (RAST/cuda_rasterizer/backward.cu:399-557).
-// Eight gradient components are summed over the warp with a halving butterfly (9 shuffles instead of
-// 40), the ninth with a plain 5-step butterfly; then nine lanes issue one atomic each into the
-// Gaussian's 48-byte accumulator record.
+// Per (warp, Gaussian) the nine per-lane partial sums are parked in a per-warp shared-memory matrix
+// [column = (buffered Gaussian, component)][lane]; every RED_K Gaussians the matrix is summed with one lane per
+// column (8 conflict-free LDS.128 each) and ONE vector of atomics -- instead of a 14-shuffle butterfly per Gaussian.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void warp_accumulate9(float v0, float v1, float v2, float v3, float v4, float v5, float v6, float v7, float v8,
-                                                 float* __restrict__ rec, int lane)
+constexpr int RED_K = 3;                 // Gaussians buffered between flushes (27 columns <= 32 lanes)
+constexpr int RED_STRIDE = 36;           // floats per column: 32 lanes + 4 pad => 16-byte units stride 9 == 1 (mod 8)
+
+__device__ __forceinline__ void red_flush(float* __restrict__ red, const uint32_t* __restrict__ rid, int nbuf, int lane, int col_g,
+                                          int col_c, float* __restrict__ acc)
 {
-    // 8 -> 4 (xor 16)
-    {
-        const bool hi = lane & 16;
-        const float s0 = hi ? v0 : v4, s1 = hi ? v1 : v5, s2 = hi ? v2 : v6, s3 = hi ? v3 : v7;
-        const float k0 = hi ? v4 : v0, k1 = hi ? v5 : v1, k2 = hi ? v6 : v2, k3 = hi ? v7 : v3;
-        v0 = k0 + __shfl_xor_sync(FULL, s0, 16);
-        v1 = k1 + __shfl_xor_sync(FULL, s1, 16);
-        v2 = k2 + __shfl_xor_sync(FULL, s2, 16);
-        v3 = k3 + __shfl_xor_sync(FULL, s3, 16);
+    __syncwarp();
+    if (lane < nbuf * 9) {
+        const float4* p = reinterpret_cast<const float4*>(red + lane * RED_STRIDE);
+        float s = 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            const float4 t = p[q];
+            s += (t.x + t.y) + (t.z + t.w);
+        }
+        atomicAdd(acc + (size_t)rid[col_g] * ACC_STRIDE + col_c, s);
     }
-    // 4 -> 2 (xor 8)
-    {
-        const bool hi = lane & 8;
-        const float s0 = hi ? v0 : v2, s1 = hi ? v1 : v3;
-        const float k0 = hi ? v2 : v0, k1 = hi ? v3 : v1;
-        v0 = k0 + __shfl_xor_sync(FULL, s0, 8);
-        v1 = k1 + __shfl_xor_sync(FULL, s1, 8);
-    }
-    // 2 -> 1 (xor 4)
-    {
-        const bool hi = lane & 4;
-        const float s0 = hi ? v0 : v1;
-        const float k0 = hi ? v1 : v0;
-        v0 = k0 + __shfl_xor_sync(FULL, s0, 4);
-    }
-    v0 += __shfl_xor_sync(FULL, v0, 2);
-    v0 += __shfl_xor_sync(FULL, v0, 1);
-    v8 += __shfl_xor_sync(FULL, v8, 16);
-    v8 += __shfl_xor_sync(FULL, v8, 8);
-    v8 += __shfl_xor_sync(FULL, v8, 4);
-    v8 += __shfl_xor_sync(FULL, v8, 2);
-    v8 += __shfl_xor_sync(FULL, v8, 1);
-    // lane holds component idx = 4*bit4 + 2*bit3 + bit2 of the 8; components 0..2 colour, 3,4 mean2D, 5,6,7 conic
-    const int idx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
-    const int slot = idx < 3 ? idx : idx + 1;  // skip slot 3 (opacity)
-    if ((lane & 3) == 0) atomicAdd(rec + slot, v0);
-    else if (lane == 1) atomicAdd(rec + 3, v8);
+    __syncwarp();
 }
 
 __global__ void __launch_bounds__(256)
@@ -569,6 +587,8 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
     __shared__ float4 s_co[8][32];
     __shared__ float4 s_rgb[8][32];
     __shared__ uint32_t s_id[8][32];
+    __shared__ __align__(16) float s_red[8][RED_K * 9 * RED_STRIDE];
+    __shared__ uint32_t s_rid[8][4];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile = blockIdx.x;
     const int tx = tile % tiles_x, ty = tile / tiles_x;
@@ -596,7 +616,10 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
     float a0 = 0.f, a1 = 0.f, a2 = 0.f;       // accum_rec
     float lc0 = 0.f, lc1 = 0.f, lc2 = 0.f;    // last colour
     float last_alpha = 0.f;
-    const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
+    float* red = s_red[warp];
+    uint32_t* rid = s_rid[warp];
+    const int col_g = lane / 9, col_c = lane - 9 * (lane / 9);
+    int nbuf = 0;
 
     for (int b = (int)((max_last - 1) >> 5); b >= 0; --b) {
         const uint32_t pos = (uint32_t)b * 32u + lane;
@@ -642,29 +665,52 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
                 rcp = fmaf(rcp, fmaf(-one_m_a, rcp, 1.0f), rcp);
                 T = T * rcp;
                 const float w = alpha * T;
-                a0 = last_alpha * lc0 + (1.f - last_alpha) * a0;
-                a1 = last_alpha * lc1 + (1.f - last_alpha) * a1;
-                a2 = last_alpha * lc2 + (1.f - last_alpha) * a2;
+                const float oml = 1.f - last_alpha;
+                a0 = fmaf(last_alpha, lc0, oml * a0);
+                a1 = fmaf(last_alpha, lc1, oml * a1);
+                a2 = fmaf(last_alpha, lc2, oml * a2);
                 lc0 = f.x; lc1 = f.y; lc2 = f.z;
                 float dL_dalpha = (f.x - a0) * d0 + (f.y - a1) * d1 + (f.z - a2) * d2;
                 v0 = w * d0; v1 = w * d1; v2 = w * d2;
-                dL_dalpha *= T;
                 last_alpha = alpha;
-                dL_dalpha += (-T_final * rcp) * bg_dot;
-                const float dL_dG = c.w * dL_dalpha;
-                const float gdx = G * dx, gdy = G * dy;
-                const float dG_ddelx = -gdx * c.x - gdy * c.y;
-                const float dG_ddely = -gdy * c.z - gdx * c.y;
-                v3 = dL_dG * dG_ddelx * ddelx_dx;
-                v4 = dL_dG * dG_ddely * ddely_dy;
-                v5 = -0.5f * gdx * dx * dL_dG;
-                v6 = -0.5f * gdx * dy * dL_dG;
-                v7 = -0.5f * gdy * dy * dL_dG;
-                v8 = G * dL_dalpha;
+                dL_dalpha = fmaf(dL_dalpha, T, (-T_final * rcp) * bg_dot);
+                const float wg = G * dL_dalpha;   // S0 term (= dL/dopacity contribution)
+                const float wdx = wg * dx, wdy = wg * dy;
+                v3 = wg; v4 = wdx; v5 = wdy;
+                v6 = wdx * dx; v7 = wdx * dy; v8 = wdy * dy;
             }
-            warp_accumulate9(v0, v1, v2, v3, v4, v5, v6, v7, v8, acc + (size_t)s_id[warp][j] * ACC_STRIDE, lane);
+            float* colp = red + nbuf * 9 * RED_STRIDE + lane;
+            colp[0 * RED_STRIDE] = v0; colp[1 * RED_STRIDE] = v1; colp[2 * RED_STRIDE] = v2;
+            colp[3 * RED_STRIDE] = v3; colp[4 * RED_STRIDE] = v4; colp[5 * RED_STRIDE] = v5;
+            colp[6 * RED_STRIDE] = v6; colp[7 * RED_STRIDE] = v7; colp[8 * RED_STRIDE] = v8;
+            if (lane == 0) rid[nbuf] = s_id[warp][j];
+            if (++nbuf == RED_K) {
+                red_flush(red, rid, nbuf, lane, col_g, col_c, acc);
+                nbuf = 0;
+            }
         }
     }
+    if (nbuf) red_flush(red, rid, nbuf, lane, col_g, col_c, acc);
+}
+
+// accumulator record -> dL/dmean2D (x,y), dL/dconic (x,y,w), dL/dopacity  (RAST/cuda_rasterizer/backward.cu:538-554)
+struct Grad2D {
+    float dcol[3], dop, dm2x, dm2y, dcx, dcy, dcw;
+};
+__device__ __forceinline__ Grad2D accum_to_grad2d(const float* __restrict__ rec, float4 co, int W, int H)
+{
+    const float4* rec4 = reinterpret_cast<const float4*>(rec);
+    const float4 r0 = rec4[0], r1 = rec4[1], r2 = rec4[2];
+    Grad2D g;
+    g.dcol[0] = r0.x; g.dcol[1] = r0.y; g.dcol[2] = r0.z;
+    g.dop = r0.w;
+    const float o = co.w;
+    g.dm2x = -o * (0.5f * W) * (co.x * r1.x + co.y * r1.y);
+    g.dm2y = -o * (0.5f * H) * (co.z * r1.y + co.y * r1.x);
+    g.dcx = -0.5f * o * r1.z;
+    g.dcy = -0.5f * o * r1.w;
+    g.dcw = -0.5f * o * r2.x;
+    return g;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -685,6 +731,7 @@ struct PreBackArgs {
     const int* radii;
     const uint8_t* clamped;
     const float* acc;
+    const float4* conic_opacity;
     float* dL_dmeans2D;
     float* dL_dcolors;
     float* dL_dopacity;
@@ -729,25 +776,23 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(PreBackArgs a)
     const float* view = s_cam;
     const float* proj = s_cam + 16;
     const float* cam = s_cam + 32;
-    const float4* rec4 = reinterpret_cast<const float4*>(a.acc + si * ACC_STRIDE);
-    const float4 r0 = rec4[0], r1 = rec4[1], r2 = rec4[2];
-    // r0 = (dcol.r, dcol.g, dcol.b, dopacity)  r1 = (dmean2D.x, dmean2D.y, dconic.x, dconic.y)  r2.x = dconic.w
+    const Grad2D g2 = accum_to_grad2d(a.acc + si * ACC_STRIDE, a.conic_opacity[si], a.W, a.H);
     const float x = a.means3D[3 * si], y = a.means3D[3 * si + 1], z = a.means3D[3 * si + 2];
     float c3[6];
 #pragma unroll
     for (int k = 0; k < 6; k++) c3[k] = a.cov3D[6 * si + k];
     float dcov[6], dmean[3];
-    lgr::cov2d_backward(x, y, z, view, c3, a.fx, a.fy, a.tanx, a.tany, r1.z, r1.w, r2.x, dcov, dmean);
-    lgr::mean2d_backward(x, y, z, proj, r1.x, r1.y, dmean);
-    a.dL_dmeans2D[3 * si] = r1.x; a.dL_dmeans2D[3 * si + 1] = r1.y; a.dL_dmeans2D[3 * si + 2] = 0.f;
-    a.dL_dcolors[3 * si] = r0.x; a.dL_dcolors[3 * si + 1] = r0.y; a.dL_dcolors[3 * si + 2] = r0.z;
-    a.dL_dopacity[si] = r0.w;
+    lgr::cov2d_backward(x, y, z, view, c3, a.fx, a.fy, a.tanx, a.tany, g2.dcx, g2.dcy, g2.dcw, dcov, dmean);
+    lgr::mean2d_backward(x, y, z, proj, g2.dm2x, g2.dm2y, dmean);
+    a.dL_dmeans2D[3 * si] = g2.dm2x; a.dL_dmeans2D[3 * si + 1] = g2.dm2y; a.dL_dmeans2D[3 * si + 2] = 0.f;
+    a.dL_dcolors[3 * si] = g2.dcol[0]; a.dL_dcolors[3 * si + 1] = g2.dcol[1]; a.dL_dcolors[3 * si + 2] = g2.dcol[2];
+    a.dL_dopacity[si] = g2.dop;
 #pragma unroll
     for (int k = 0; k < 6; k++) a.dL_dcov3D[6 * si + k] = dcov[k];
 
     if (a.shs) {
         const unsigned cb = a.clamped[i];
-        const float dRGB[3] = {(cb & 1u) ? 0.f : r0.x, (cb & 2u) ? 0.f : r0.y, (cb & 4u) ? 0.f : r0.z};
+        const float dRGB[3] = {(cb & 1u) ? 0.f : g2.dcol[0], (cb & 2u) ? 0.f : g2.dcol[1], (cb & 4u) ? 0.f : g2.dcol[2]};
         const float* sh = a.shs + si * a.M * 3;
         if (a.M == 16) {
             float v[48], o[48];
@@ -944,7 +989,7 @@ int forward_impl(const lgr_view* v, int P, int M, const float* means3D, const fl
                                                               bin.point_list, R, 0, bits, stream));
             }
             ProfScope ps(ST_RANGES, stream);
-            ranges_kernel<uint32_t><<<(R + 255) / 256, 256, 0, stream>>>(R, (const uint32_t*)bin.keys_sorted, img.ranges);
+            ranges_kernel<uint32_t><<<(gx * gy + 255) / 256, 256, 0, stream>>>(R, gx * gy, (const uint32_t*)bin.keys_sorted, img.ranges);
         } else {
             {
                 ProfScope ps(ST_EMIT, stream);
@@ -959,7 +1004,7 @@ int forward_impl(const lgr_view* v, int P, int M, const float* means3D, const fl
                                                               bin.point_list, R, 0, bits, stream));
             }
             ProfScope ps(ST_RANGES, stream);
-            ranges_kernel<uint16_t><<<(R + 255) / 256, 256, 0, stream>>>(R, (const uint16_t*)bin.keys_sorted, img.ranges);
+            ranges_kernel<uint16_t><<<(gx * gy + 255) / 256, 256, 0, stream>>>(R, gx * gy, (const uint16_t*)bin.keys_sorted, img.ranges);
         }
         LGR_LAUNCH_CHECK("ranges_kernel", debug, stream);
     }
@@ -1114,7 +1159,7 @@ int lgr_backward(const lgr_view* v, int P, int M, int num_rendered, const float*
     a.means3D = means3D; a.scales = scales; a.rotations = rotations; a.shs = shs;
     a.cov3D = cov3D_precomp ? cov3D_precomp : geo.cov3D;
     a.view = v->viewmatrix; a.proj = v->projmatrix; a.campos = v->campos;
-    a.radii = radii; a.clamped = geo.clamped; a.acc = geo.grad_acc;
+    a.radii = radii; a.clamped = geo.clamped; a.acc = geo.grad_acc; a.conic_opacity = geo.conic_opacity;
     a.dL_dmeans2D = dL_dmeans2D; a.dL_dcolors = dL_dcolors; a.dL_dopacity = dL_dopacity; a.dL_dmeans3D = dL_dmeans3D;
     a.dL_dcov3D = dL_dcov3D; a.dL_dsh = dL_dsh; a.dL_dscales = dL_dscales; a.dL_drot = dL_drotations;
     {
