@@ -237,17 +237,40 @@ def main():
         allreduce_grads()
         return loss
 
-    def step_e2e(step):
+    # e2e: every step's camera and target image start in pinned HOST memory.  The copies are issued one step ahead on a
+    # separate stream (copy engine) into a 2-deep device ring, so they overlap the previous step's kernels; the
+    # compute stream waits on the copy's event before it touches the data.
+    copy_stream = torch.cuda.Stream(device=dev)
+    ring = [dict(wv=torch.empty(4, 4, device=dev), fp=torch.empty(4, 4, device=dev), cc=torch.empty(3, device=dev),
+                 tgt=torch.empty(3, H, W, device=dev), ev=torch.cuda.Event(), used=torch.cuda.Event()) for _ in range(2)]
+    e2e_cam = TorchCamera(cams_np[0], dev)
+
+    def prefetch(step):
+        slot = ring[step % 2]
         i = view_index(step)
-        cam = cams[i]
         wv, fp, cc = cam_host[i]
-        cam.world_view_transform.copy_(wv, non_blocking=True)      # H2D: this step's camera
-        cam.full_proj_transform.copy_(fp, non_blocking=True)
-        cam.camera_center.copy_(cc, non_blocking=True)
-        tgt = targets_host[i % len(targets_host)].to(dev, non_blocking=True)  # H2D: this step's target image
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(slot["used"])          # the slot's previous consumer has finished
+            slot["wv"].copy_(wv, non_blocking=True)        # H2D: this step's camera
+            slot["fp"].copy_(fp, non_blocking=True)
+            slot["cc"].copy_(cc, non_blocking=True)
+            slot["tgt"].copy_(targets_host[i % len(targets_host)], non_blocking=True)  # H2D: this step's target image
+            slot["ev"].record(copy_stream)
+
+    e2e_state = {"primed": -1}
+
+    def step_e2e(step):
+        if e2e_state["primed"] != step:
+            prefetch(step)
+        slot = ring[step % 2]
+        prefetch(step + 1)
+        e2e_state["primed"] = step + 1
+        torch.cuda.current_stream().wait_event(slot["ev"])
+        e2e_cam.world_view_transform, e2e_cam.full_proj_transform, e2e_cam.camera_center = slot["wv"], slot["fp"], slot["cc"]
         zero_grads()
-        loss = train_view(render_fn, cam, pc, pipe, bg, tgt)
+        loss = train_view(render_fn, e2e_cam, pc, pipe, bg, slot["tgt"])
         allreduce_grads()
+        slot["used"].record()
         return float(loss.item())                                   # D2H: the step's result
 
     def barrier():

@@ -153,6 +153,12 @@ size_t lgr_binning_layout(int num_rendered, int width, int height, size_t* out, 
 /* Kernel launches issued by this library since load (for bench.py's gpu_launches). */
 uint64_t lgr_launch_count(void);
 
+/* Exact tile-level culling at binning time (default on): (tile, Gaussian) instances in which no pixel can reach
+ * alpha >= 1/255 are not listed.  Images, gradients and significance are unchanged; only the internal lists shrink.
+ * Turn it off to obtain per-tile lists identical to the reference's (tests).  num_rendered always reports the
+ * reference's value.  The geometry blob starts with two int32: [0] instances listed, [1] the reference's num_rendered. */
+int lgr_set_tile_culling(int on);
+
 /* Optional per-stage device timing: when enabled every launch is bracketed by CUDA events on its stream.
  * lgr_profile_collect() synchronises the device, writes the accumulated milliseconds and launch counts of each
  * stage (index < lgr_profile_stage_count()) and resets them.  Timing mode adds event overhead; do not use it

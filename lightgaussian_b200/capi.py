@@ -168,6 +168,11 @@ def binning_layout(R: int, W: int, H: int):
     return dict(point_list=int(out[0])), int(total)
 
 
+def set_tile_culling(on: bool):
+    """exact tile-level culling at binning time (default on); off = per-tile lists identical to the reference's"""
+    check(load().lgr_set_tile_culling(int(on)), "lgr_set_tile_culling")
+
+
 def profile_enable(on: bool):
     load().lgr_profile_enable(int(on))
 

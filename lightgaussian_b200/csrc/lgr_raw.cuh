@@ -163,6 +163,7 @@ __global__ void __launch_bounds__(256) preprocess_raw_kernel(RawArgs a, int* __r
         if (!visible) {
             radii[i] = 0;
             g.tiles_touched[i] = 0;
+            g.tiles_kept[i] = 0;
             g.depth_keys[i] = 0xffffffffu;
             g.clamped[i] = 0;
         } else {
@@ -170,8 +171,15 @@ __global__ void __launch_bounds__(256) preprocess_raw_kernel(RawArgs a, int* __r
             g.depth[i] = geo.depth;
             g.depth_keys[i] = __float_as_uint(geo.depth);
             g.means2D[i] = make_float2(geo.px, geo.py);
-            g.conic_opacity[i] = make_float4(geo.conic_x, geo.conic_y, geo.conic_z, act_sigmoid(a.opacity[i]));
-            g.tiles_touched[i] = (uint32_t)((geo.rect.y1 - geo.rect.y0) * (geo.rect.x1 - geo.rect.x0));
+            const float4 co = make_float4(geo.conic_x, geo.conic_y, geo.conic_z, act_sigmoid(a.opacity[i]));
+            g.conic_opacity[i] = co;
+            const uint32_t area = (uint32_t)((geo.rect.y1 - geo.rect.y0) * (geo.rect.x1 - geo.rect.x0));
+            g.tiles_touched[i] = area;
+            unsigned long long mask;
+            uint32_t kept;
+            tile_keep_mask(geo, co, a.W, a.H, mask, kept);
+            g.tiles_kept[i] = kept;
+            g.keep_mask[i] = mask;
         }
     }
     if (!any_vis) return;

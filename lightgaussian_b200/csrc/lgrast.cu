@@ -120,23 +120,31 @@ struct GeometryState {
     float4* rgb;               // [P] xyz = colour fed to the blend
     float* cov3D;              // [6P]
     uint8_t* clamped;          // [P] bit c = channel c clamped
-    uint32_t* tiles_touched;   // [P]
+    uint32_t* tiles_touched;   // [P] tile-rectangle area (the reference's definition)
+    uint32_t* tiles_kept;      // [P] instances actually emitted after exact tile culling (<= tiles_touched)
+    unsigned long long* keep_mask;  // [P] bit b set = rectangle tile b (row-major) is kept; all ones when the rectangle has > 64 tiles
     uint32_t* sorted_ids;      // [P] Gaussian ids in (depth bits, id) order; culled ones last
     uint32_t* depth_keys;      // [P] scratch
     uint32_t* depth_keys_sorted;  // [P] scratch
     uint32_t* iota;            // [P] scratch
-    uint32_t* offsets;         // [P] inclusive scan of tiles_touched in sorted order
+    unsigned long long* offsets;  // [P] inclusive scan in sorted order: low word kept instances, high word rectangle areas
     float* grad_acc;           // [12P] backward accumulator records
-    int* num_rendered;         // [1]
+    int* num_rendered;         // header: [0] instances emitted (kept), [1] sum of tiles_touched (the reference's num_rendered)
     char* cub_temp;
     size_t cub_temp_bytes;
     size_t offs[8];
     size_t total;
 };
 
+// scan input in depth order: low 32 bits = instances kept, high 32 bits = tile-rectangle area, so ONE inclusive scan yields
+// the emit offsets (low) and the reference's num_rendered (high word of the last element)
 struct TilesTouchedOp {
-    const uint32_t* tiles;
-    __host__ __device__ __forceinline__ uint32_t operator()(const uint32_t& id) const { return tiles[id]; }
+    const uint32_t* kept;
+    const uint32_t* touched;
+    __host__ __device__ __forceinline__ unsigned long long operator()(const uint32_t& id) const
+    {
+        return (unsigned long long)kept[id] | ((unsigned long long)touched[id] << 32);
+    }
 };
 
 GeometryState carve_geometry(char* base, size_t P)
@@ -152,16 +160,18 @@ GeometryState carve_geometry(char* base, size_t P)
     g.clamped = c.take<uint8_t>(P, &g.offs[5]);
     g.tiles_touched = c.take<uint32_t>(P, &g.offs[6]);
     g.sorted_ids = c.take<uint32_t>(P, &g.offs[7]);
+    g.tiles_kept = c.take<uint32_t>(P);
+    g.keep_mask = c.take<unsigned long long>(P);
     g.depth_keys = c.take<uint32_t>(P);
     g.depth_keys_sorted = c.take<uint32_t>(P);
     g.iota = c.take<uint32_t>(P);
-    g.offsets = c.take<uint32_t>(P);
+    g.offsets = c.take<unsigned long long>(P);
     g.grad_acc = c.take<float>(ACC_STRIDE * P);
     size_t sort_bytes = 0, scan_bytes = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr,
                                     (uint32_t*)nullptr, (int)P, 0, 32);
-    cub::TransformInputIterator<uint32_t, TilesTouchedOp, const uint32_t*> it(nullptr, TilesTouchedOp{nullptr});
-    cub::DeviceScan::InclusiveSum(nullptr, scan_bytes, it, (uint32_t*)nullptr, (int)P);
+    cub::TransformInputIterator<unsigned long long, TilesTouchedOp, const uint32_t*> it(nullptr, TilesTouchedOp{nullptr, nullptr});
+    cub::DeviceScan::InclusiveSum(nullptr, scan_bytes, it, (unsigned long long*)nullptr, (int)P);
     g.cub_temp_bytes = sort_bytes > scan_bytes ? sort_bytes : scan_bytes;
     g.cub_temp = c.take<char>(g.cub_temp_bytes);
     g.total = align_up(c.off, 256);
@@ -235,6 +245,59 @@ BinningState carve_binning(char* base, size_t R, int W, int H)
 }
 
 // ------------------------------------------------------------------------------------------------
+// Exact, conservative sub-tile culling.  Returns true when NO pixel centre in [rx0,rx1]x[ry0,ry1] can
+// reach alpha >= 1/255 for this Gaussian, i.e. when the reference would skip every pair at
+// RAST/cuda_rasterizer/forward.cu:345-347.  A 1% margin on alpha covers all rounding in this test.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool subtile_cull(float gxp, float gyp, float4 co, float rx0, float rx1, float ry0, float ry1)
+{
+    const float A = co.x, B = co.y, Cc = co.z;
+    const float t = 257.55f * co.w;  // 255 * 1.01 * opacity
+    if (t <= 1.0f) return true;      // alpha <= opacity < 1/255 everywhere
+    const float dx_lo = gxp - rx1, dx_hi = gxp - rx0, dy_lo = gyp - ry1, dy_hi = gyp - ry0;
+    const float cx = fminf(fmaxf(0.f, dx_lo), dx_hi), cy = fminf(fmaxf(0.f, dy_lo), dy_hi);
+    if (cx == 0.f && cy == 0.f) return false;                        // centre inside the sub-tile
+    if (!(A > 0.f && Cc > 0.f && A * Cc - B * B > 0.f)) return false;  // not positive definite: never cull
+    const float thr = __logf(t);
+    float qmin = 3.0e38f;
+    if (cx != 0.f) {
+        const float dy = fminf(fmaxf(__fdividef(-B * cx, Cc), dy_lo), dy_hi);
+        qmin = 0.5f * (A * cx * cx + Cc * dy * dy) + B * cx * dy;
+    }
+    if (cy != 0.f) {
+        const float dx = fminf(fmaxf(__fdividef(-B * cy, A), dx_lo), dx_hi);
+        qmin = fminf(qmin, 0.5f * (A * dx * dx + Cc * cy * cy) + B * dx * cy);
+    }
+    return qmin > thr;
+}
+
+// Exact tile-level culling at binning time: tile b of a Gaussian's rectangle is dropped when no pixel centre inside
+// it can reach alpha >= 1/255 -- every (pixel, Gaussian) pair of such an instance is skipped by the reference
+// (forward.cu:345-347), so the image is unchanged while the instance list, its sort and the per-tile walks shrink.
+// Rectangles above 64 tiles (huge splats) are kept whole.
+__device__ bool g_tile_cull_enabled = true;
+
+__device__ __forceinline__ void tile_keep_mask(const lgr::Geom& geo, float4 co, int W, int H, unsigned long long& mask, uint32_t& kept)
+{
+    const int w = geo.rect.x1 - geo.rect.x0, h = geo.rect.y1 - geo.rect.y0;
+    const int area = w * h;
+    if (area > 64 || !g_tile_cull_enabled) {
+        mask = ~0ull;
+        kept = (uint32_t)area;
+        return;
+    }
+    mask = 0ull;
+    int tx = geo.rect.x0, ty = geo.rect.y0;
+    for (int b = 0; b < area; b++) {
+        const float rx0 = (float)(tx * LGR_TILE), rx1 = (float)min(tx * LGR_TILE + LGR_TILE - 1, W - 1);
+        const float ry0 = (float)(ty * LGR_TILE), ry1 = (float)min(ty * LGR_TILE + LGR_TILE - 1, H - 1);
+        if (!subtile_cull(geo.px, geo.py, co, rx0, rx1, ry0, ry1)) mask |= 1ull << b;
+        if (++tx == geo.rect.x1) { tx = geo.rect.x0; ++ty; }
+    }
+    kept = (uint32_t)__popcll(mask);
+}
+
+// ------------------------------------------------------------------------------------------------
 // K1  preprocess
 // ------------------------------------------------------------------------------------------------
 struct PreprocessArgs {
@@ -295,6 +358,7 @@ __global__ void __launch_bounds__(256) preprocess_kernel(PreprocessArgs a, int* 
     if (!visible) {
         radii[i] = 0;
         g.tiles_touched[i] = 0;
+        g.tiles_kept[i] = 0;
         g.depth_keys[i] = 0xffffffffu;
         g.clamped[i] = 0;
         return;
@@ -329,7 +393,13 @@ __global__ void __launch_bounds__(256) preprocess_kernel(PreprocessArgs a, int* 
     g.conic_opacity[i] = make_float4(geo.conic_x, geo.conic_y, geo.conic_z, a.opacities[i]);
     g.rgb[i] = make_float4(rgb[0], rgb[1], rgb[2], 0.f);
     g.clamped[i] = (uint8_t)clamp_bits;
-    g.tiles_touched[i] = (uint32_t)((geo.rect.y1 - geo.rect.y0) * (geo.rect.x1 - geo.rect.x0));
+    const uint32_t area = (uint32_t)((geo.rect.y1 - geo.rect.y0) * (geo.rect.x1 - geo.rect.x0));
+    g.tiles_touched[i] = area;
+    unsigned long long mask;
+    uint32_t kept;
+    tile_keep_mask(geo, make_float4(geo.conic_x, geo.conic_y, geo.conic_z, a.opacities[i]), a.W, a.H, mask, kept);
+    g.tiles_kept[i] = kept;
+    g.keep_mask[i] = mask;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -340,23 +410,25 @@ __global__ void __launch_bounds__(256) preprocess_kernel(PreprocessArgs a, int* 
 // warp's run offsets, so key/id stores are fully coalesced whatever the splat sizes are (the reference's one thread
 // per Gaussian loop is serial in the splat area, rasterizer_impl.cu:98-109).
 template <typename KeyT>
-__global__ void __launch_bounds__(256) emit_kernel(int P, const uint32_t* __restrict__ sorted_ids, const uint32_t* __restrict__ offsets,
-                                                   const uint32_t* __restrict__ tiles_touched, const float2* __restrict__ means2D,
-                                                   const int* __restrict__ radii, int gx, int gy, KeyT* __restrict__ keys,
-                                                   uint32_t* __restrict__ ids)
+__global__ void __launch_bounds__(256) emit_kernel(int P, const uint32_t* __restrict__ sorted_ids, const unsigned long long* __restrict__ offsets,
+                                                   const uint32_t* __restrict__ tiles_kept, const unsigned long long* __restrict__ keep_mask,
+                                                   const float2* __restrict__ means2D, const int* __restrict__ radii, int gx, int gy,
+                                                   KeyT* __restrict__ keys, uint32_t* __restrict__ ids)
 {
     const int lane = threadIdx.x & 31;
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t id = 0, cnt = 0, off = 0;
     int x0 = 0, y0 = 0, w = 1;
+    unsigned long long mask = ~0ull;
     if (k < P) {
         id = sorted_ids[k];
-        cnt = tiles_touched[id];
-        off = offsets[k] - cnt;  // offsets = inclusive scan in sorted order
+        cnt = tiles_kept[id];
+        off = (uint32_t)offsets[k] - cnt;  // low word of the inclusive scan = kept instances up to and including k
         if (cnt) {
             const float2 p = means2D[id];
             const lgr::TileRect r = lgr::tile_rect(p.x, p.y, radii[id], gx, gy);
             x0 = r.x0; y0 = r.y0; w = r.x1 - r.x0;
+            mask = keep_mask[id];
         }
     }
     // lanes past P inherit the running offset so that `off` stays non-decreasing across the warp
@@ -383,8 +455,14 @@ __global__ void __launch_bounds__(256) emit_kernel(int P, const uint32_t* __rest
         const uint32_t o_off = __shfl_sync(FULL, off, lo);
         const uint32_t o_id = __shfl_sync(FULL, id, lo);
         const int o_x0 = __shfl_sync(FULL, x0, lo), o_y0 = __shfl_sync(FULL, y0, lo), o_w = __shfl_sync(FULL, w, lo);
+        const unsigned long long o_mask = __shfl_sync(FULL, mask, lo);
         if (j < span_end) {
-            const int local = (int)(j - o_off);
+            int local = (int)(j - o_off);
+            if (o_mask != ~0ull) {  // local-th kept tile of the rectangle
+                const uint32_t mlo = (uint32_t)o_mask;
+                const int clo = __popc(mlo);
+                local = local < clo ? (int)__fns(mlo, 0, local + 1) : 32 + (int)__fns((uint32_t)(o_mask >> 32), 0, local - clo + 1);
+            }
             const int ry = local / o_w, rx = local - ry * o_w;
             keys[j] = (KeyT)((o_y0 + ry) * gx + (o_x0 + rx));
             ids[j] = o_id;
@@ -410,33 +488,6 @@ __global__ void __launch_bounds__(256) ranges_kernel(int R, int tiles, const Key
     };
     const uint32_t a = lower((uint32_t)t), b = lower((uint32_t)t + 1u);
     ranges[t] = (b > a) ? make_uint2(a, b) : make_uint2(0u, 0u);
-}
-
-// ------------------------------------------------------------------------------------------------
-// Exact, conservative sub-tile culling.  Returns true when NO pixel centre in [rx0,rx1]x[ry0,ry1] can
-// reach alpha >= 1/255 for this Gaussian, i.e. when the reference would skip every pair at
-// RAST/cuda_rasterizer/forward.cu:345-347.  A 1% margin on alpha covers all rounding in this test.
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool subtile_cull(float gxp, float gyp, float4 co, float rx0, float rx1, float ry0, float ry1)
-{
-    const float A = co.x, B = co.y, Cc = co.z;
-    const float t = 257.55f * co.w;  // 255 * 1.01 * opacity
-    if (t <= 1.0f) return true;      // alpha <= opacity < 1/255 everywhere
-    const float dx_lo = gxp - rx1, dx_hi = gxp - rx0, dy_lo = gyp - ry1, dy_hi = gyp - ry0;
-    const float cx = fminf(fmaxf(0.f, dx_lo), dx_hi), cy = fminf(fmaxf(0.f, dy_lo), dy_hi);
-    if (cx == 0.f && cy == 0.f) return false;                        // centre inside the sub-tile
-    if (!(A > 0.f && Cc > 0.f && A * Cc - B * B > 0.f)) return false;  // not positive definite: never cull
-    const float thr = __logf(t);
-    float qmin = 3.0e38f;
-    if (cx != 0.f) {
-        const float dy = fminf(fmaxf(__fdividef(-B * cx, Cc), dy_lo), dy_hi);
-        qmin = 0.5f * (A * cx * cx + Cc * dy * dy) + B * cx * dy;
-    }
-    if (cy != 0.f) {
-        const float dx = fminf(fmaxf(__fdividef(-B * cy, A), dx_lo), dx_hi);
-        qmin = fminf(qmin, 0.5f * (A * dx * dx + Cc * cy * cy) + B * dx * cy);
-    }
-    return qmin > thr;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -920,7 +971,7 @@ int forward_impl(const lgr_view* v, int P, int M, const float* means3D, const fl
     img = carve_image(img_blob, W, H);
     LGR_CUDA_TRY(cudaMemsetAsync(img.ranges, 0, sizeof(uint2) * (size_t)gx * gy, stream));
 
-    int R = 0;
+    int R = 0, R_ref = 0;
     BinningState bin;
     if (P > 0) {
         PreprocessArgs a;
@@ -955,16 +1006,18 @@ int forward_impl(const lgr_view* v, int P, int M, const float* means3D, const fl
             LGR_CUDA_TRY(cub::DeviceRadixSort::SortPairs(geo.cub_temp, tmp, (const uint32_t*)geo.depth_keys, geo.depth_keys_sorted,
                                                           (const uint32_t*)geo.iota, geo.sorted_ids, P, 0, 32, stream));
         }
-        cub::TransformInputIterator<uint32_t, TilesTouchedOp, const uint32_t*> it(geo.sorted_ids, TilesTouchedOp{geo.tiles_touched});
+        cub::TransformInputIterator<unsigned long long, TilesTouchedOp, const uint32_t*> it(geo.sorted_ids, TilesTouchedOp{geo.tiles_kept, geo.tiles_touched});
         tmp = geo.cub_temp_bytes;
         {
             ProfScope ps(ST_SCAN, stream);
             LGR_CUDA_TRY(cub::DeviceScan::InclusiveSum(geo.cub_temp, tmp, it, geo.offsets, P, stream));
         }
         int* host_R = t_pinned.get();
-        LGR_CUDA_TRY(cudaMemcpyAsync(host_R, geo.offsets + (P - 1), sizeof(int), cudaMemcpyDeviceToHost, stream));
+        LGR_CUDA_TRY(cudaMemcpyAsync(geo.num_rendered, geo.offsets + (P - 1), 2 * sizeof(int), cudaMemcpyDeviceToDevice, stream));
+        LGR_CUDA_TRY(cudaMemcpyAsync(host_R, geo.offsets + (P - 1), 2 * sizeof(int), cudaMemcpyDeviceToHost, stream));
         LGR_CUDA_TRY(cudaStreamSynchronize(stream));
-        R = *host_R;
+        R = host_R[0];       // instances actually emitted (after exact tile culling)
+        R_ref = host_R[1];   // the reference's num_rendered: sum of the tile-rectangle areas
     }
     bin = carve_binning(nullptr, (size_t)R, W, H);
     char* bin_blob = binning_alloc(binning_user, bin.total);
@@ -978,8 +1031,8 @@ int forward_impl(const lgr_view* v, int P, int M, const float* means3D, const fl
         if (bin.wide_keys) {
             {
                 ProfScope ps(ST_EMIT, stream);
-                emit_kernel<uint32_t><<<blocks, 256, 0, stream>>>(P, geo.sorted_ids, geo.offsets, geo.tiles_touched, geo.means2D, radii,
-                                                                   gx, gy, (uint32_t*)bin.keys_unsorted, bin.ids_unsorted);
+                emit_kernel<uint32_t><<<blocks, 256, 0, stream>>>(P, geo.sorted_ids, geo.offsets, geo.tiles_kept, geo.keep_mask, geo.means2D,
+                                                                   radii, gx, gy, (uint32_t*)bin.keys_unsorted, bin.ids_unsorted);
             }
             LGR_LAUNCH_CHECK("emit_kernel", debug, stream);
             {
@@ -993,8 +1046,8 @@ int forward_impl(const lgr_view* v, int P, int M, const float* means3D, const fl
         } else {
             {
                 ProfScope ps(ST_EMIT, stream);
-                emit_kernel<uint16_t><<<blocks, 256, 0, stream>>>(P, geo.sorted_ids, geo.offsets, geo.tiles_touched, geo.means2D, radii,
-                                                                   gx, gy, (uint16_t*)bin.keys_unsorted, bin.ids_unsorted);
+                emit_kernel<uint16_t><<<blocks, 256, 0, stream>>>(P, geo.sorted_ids, geo.offsets, geo.tiles_kept, geo.keep_mask, geo.means2D,
+                                                                   radii, gx, gy, (uint16_t*)bin.keys_unsorted, bin.ids_unsorted);
             }
             LGR_LAUNCH_CHECK("emit_kernel", debug, stream);
             {
@@ -1029,7 +1082,7 @@ int forward_impl(const lgr_view* v, int P, int M, const float* means3D, const fl
         LGR_LAUNCH_CHECK("score_kernel", debug, stream);
     }
     (void)N;
-    *num_rendered = R;
+    *num_rendered = R_ref;
     return LGR_OK;
 }
 
@@ -1040,6 +1093,13 @@ extern "C" {
 int lgr_abi_version(void) { return LGR_ABI_VERSION; }
 const char* lgr_last_error(void) { return g_last_error.c_str(); }
 uint64_t lgr_launch_count(void) { return g_launches.load(); }
+
+int lgr_set_tile_culling(int on)
+{
+    const bool v = on != 0;
+    LGR_CUDA_TRY(cudaMemcpyToSymbol(g_tile_cull_enabled, &v, sizeof(bool)));
+    return LGR_OK;
+}
 
 int lgr_profile_enable(int on)
 {

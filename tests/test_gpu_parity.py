@@ -63,7 +63,7 @@ def test_binning_and_blend_vs_oracle(name):
     """binning order identical; image within 1e-4 wherever no threshold test is within rounding noise
     (the oracle's exp() is glibc's, the GPU's is libdevice's on MUFU.EX2)."""
     act, view, _ = make_config(name)
-    ours = run_ours(view, act, count=True)
+    ours = run_ours(view, act, count=True, tile_cull=False)
     o = Oracle()
     ref = oracle_from_geometry(o, view, ours["geom"], count=True)
     np.testing.assert_array_equal(ours["point_list"], ref["point_list"])
@@ -150,7 +150,7 @@ needs_ref = pytest.mark.skipif(not util.have_ref(), reason="oracle/_ref/libref_r
 @pytest.mark.parametrize("name", list(CONFIGS))
 def test_forward_vs_reference_kernels(name):
     act, view, _ = make_config(name)
-    ours = run_ours(view, act)
+    ours = run_ours(view, act, tile_cull=False)
     ref = run_ref(view, act)
     assert ours["num_rendered"] == ref["num_rendered"]
     np.testing.assert_array_equal(ours["radii"], ref["radii"])
@@ -193,6 +193,32 @@ def test_significance_vs_reference_kernels():
     np.testing.assert_array_equal(ours["color"], plain["color"])
 
 
+@pytest.mark.parametrize("name", list(CONFIGS))
+def test_tile_culling_changes_lists_but_not_results(name):
+    """The product default drops (tile, Gaussian) instances in which no pixel can reach alpha >= 1/255.  Outputs must be
+    bit-identical to the unculled run (= the reference's lists), the kept list an order-preserving subsequence."""
+    act, view, dpix = make_config(name)
+    full = run_ours(view, act, count=True, tile_cull=False)
+    cull = run_ours(view, act, count=True)
+    assert cull["num_rendered"] == full["num_rendered"]               # API value = the reference's definition
+    assert cull["num_listed"] <= full["num_listed"] == full["num_rendered"]
+    np.testing.assert_array_equal(cull["color"], full["color"])
+    np.testing.assert_array_equal(cull["final_T"], full["final_T"])
+    np.testing.assert_array_equal(cull["gaussians_count"], full["gaussians_count"])
+    np.testing.assert_array_equal(cull["radii"], full["radii"])
+    for t in range(full["ranges"].shape[0]):
+        a = full["point_list"][full["ranges"][t, 0]:full["ranges"][t, 1]].tolist()
+        b = cull["point_list"][cull["ranges"][t, 0]:cull["ranges"][t, 1]].tolist()
+        it = iter(a)
+        assert all(x in it for x in b), f"tile {t}: culled list is not an ordered subsequence"
+    gf = run_ours(view, act, dL_dpix=dpix, tile_cull=False)["grads"]
+    gc = run_ours(view, act, dL_dpix=dpix)["grads"]
+    for k in gf:
+        assert rel_inf(gc[k], gf[k]) <= GRAD_TOL, k
+    if name == "outside":
+        assert cull["num_listed"] < full["num_listed"]
+
+
 # ------------------------------------------------------------------------------------------------
 # edge cases (empty / ragged / degenerate inputs)
 # ------------------------------------------------------------------------------------------------
@@ -222,12 +248,15 @@ def test_ragged_image_sizes(wh):
     W, H = wh
     scene = make_scene(500, seed=21, scale_mult=3.0)
     view = util.view_from_camera(make_cameras(3, W, H)[1], (0.1, 0.2, 0.3), 3, 1.0)
-    ours = run_ours(view, scene["act"], count=True)
+    ours = run_ours(view, scene["act"], count=True, tile_cull=False)
     o = Oracle()
     ref = oracle_from_geometry(o, view, ours["geom"], count=True)
     err = np.abs(ours["color"] - ref["color"]).max(axis=0)
     assert err[~ref["fragile"]].max(initial=0.0) <= RGB_TOL
     np.testing.assert_array_equal(ours["point_list"], ref["point_list"])
+    culled = run_ours(view, scene["act"], count=True)
+    np.testing.assert_array_equal(culled["color"], ours["color"])
+    np.testing.assert_array_equal(culled["gaussians_count"], ours["gaussians_count"])
 
 
 def test_single_gaussian_and_huge_splat():
@@ -241,7 +270,7 @@ def test_single_gaussian_and_huge_splat():
     view = util.view_from_camera(make_cameras(3, W, H)[1], (0.0, 0.0, 0.0), 0, 1.0)
     ours = run_ours(view, act, count=True)
     tiles = ((W + 15) // 16) * ((H + 15) // 16)
-    assert ours["num_rendered"] == tiles
+    assert ours["num_rendered"] == tiles == ours["num_listed"]
     assert ours["gaussians_count"][0] == W * H
     assert ours["geom"]["clamped_bits"][0] == 4  # blue channel clamped at 0
     assert np.all(ours["color"][2] == 0)

@@ -51,7 +51,21 @@ def _empty():
     return torch.Tensor([])
 
 
-def run_ours(view: View, act: dict, count=False, dL_dpix=None, colors_precomp=None, cov3D_precomp=None, debug=False):
+def run_ours(view: View, act: dict, count=False, dL_dpix=None, colors_precomp=None, cov3D_precomp=None, debug=False, tile_cull=True):
+    """tile_cull=False makes the per-tile lists identical to the reference's (needed to compare point_list / ranges /
+    n_contrib); the product default (True) lists only instances that can contribute."""
+    import torch
+    from lightgaussian_b200 import capi
+    from lightgaussian_b200.rasterizer import _C
+    dev = "cuda"
+    capi.set_tile_culling(tile_cull)
+    try:
+        return _run_ours(view, act, count, dL_dpix, colors_precomp, cov3D_precomp, debug)
+    finally:
+        capi.set_tile_culling(True)
+
+
+def _run_ours(view, act, count, dL_dpix, colors_precomp, cov3D_precomp, debug):
     import torch
     from lightgaussian_b200 import capi
     from lightgaussian_b200.rasterizer import _C
@@ -76,8 +90,11 @@ def run_ours(view: View, act: dict, count=False, dL_dpix=None, colors_precomp=No
     if P > 0:
         gl, _ = capi.geometry_layout(P)
         il, _ = capi.image_layout(view.W, view.H)
-        bl, _ = capi.binning_layout(R, view.W, view.H)
         gb, ib, bb = geom.cpu().numpy(), img.cpu().numpy(), binning.cpu().numpy()
+        hdr = np.frombuffer(gb, dtype=np.int32, count=2, offset=0)
+        assert int(hdr[1]) == R, (hdr, R)                 # header[1] = the reference's num_rendered
+        out["num_listed"] = n_listed = int(hdr[0])        # header[0] = instances actually listed (<= R)
+        bl, _ = capi.binning_layout(n_listed, view.W, view.H)
         N = view.W * view.H
         tiles = ((view.W + 15) // 16) * ((view.H + 15) // 16)
 
@@ -93,7 +110,7 @@ def run_ours(view: View, act: dict, count=False, dL_dpix=None, colors_precomp=No
         out["final_T"] = arr(ib, il["final_T"], np.float32, N)
         out["n_contrib"] = arr(ib, il["n_contrib"], np.uint32, N)
         out["ranges"] = arr(ib, il["ranges"], np.uint32, 2 * tiles).reshape(tiles, 2)
-        out["point_list"] = arr(bb, bl["point_list"], np.uint32, R) if R > 0 else np.zeros(0, np.uint32)
+        out["point_list"] = arr(bb, bl["point_list"], np.uint32, n_listed) if n_listed > 0 else np.zeros(0, np.uint32)
     if dL_dpix is not None and not count:
         g = _C.rasterize_gaussians_backward(bg, means3D, radii, colors, scales, rots, view.scale_modifier, cov, vm, pm, view.tanfovx,
                                             view.tanfovy, _t(dL_dpix), shs, view.sh_degree, cp, geom, R, binning, img, debug)
