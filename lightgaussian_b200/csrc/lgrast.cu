@@ -281,20 +281,45 @@ __device__ __forceinline__ void tile_keep_mask(const lgr::Geom& geo, float4 co, 
 {
     const int w = geo.rect.x1 - geo.rect.x0, h = geo.rect.y1 - geo.rect.y0;
     const int area = w * h;
-    if (area > 64 || !g_tile_cull_enabled) {
-        mask = ~0ull;
-        kept = (uint32_t)area;
+    mask = ~0ull;
+    kept = (uint32_t)area;
+    if (area > 64 || !g_tile_cull_enabled) return;
+    // same test as subtile_cull(), with everything that does not depend on the tile hoisted out of the loop
+    const float A = co.x, B = co.y, Cc = co.z;
+    const float t = 257.55f * co.w;
+    if (t <= 1.0f) {  // alpha <= opacity < 1/255 everywhere: the Gaussian is listed nowhere
+        mask = 0ull;
+        kept = 0;
         return;
     }
-    mask = 0ull;
-    int tx = geo.rect.x0, ty = geo.rect.y0;
-    for (int b = 0; b < area; b++) {
-        const float rx0 = (float)(tx * LGR_TILE), rx1 = (float)min(tx * LGR_TILE + LGR_TILE - 1, W - 1);
-        const float ry0 = (float)(ty * LGR_TILE), ry1 = (float)min(ty * LGR_TILE + LGR_TILE - 1, H - 1);
-        if (!subtile_cull(geo.px, geo.py, co, rx0, rx1, ry0, ry1)) mask |= 1ull << b;
-        if (++tx == geo.rect.x1) { tx = geo.rect.x0; ++ty; }
+    if (!(A > 0.f && Cc > 0.f && A * Cc - B * B > 0.f)) return;
+    const float thr = __logf(t);
+    const float nbc = __fdividef(-B, Cc), nba = __fdividef(-B, A), hA = 0.5f * A, hC = 0.5f * Cc;
+    unsigned long long m = 0ull;
+    int b = 0;
+    for (int ty = geo.rect.y0; ty < geo.rect.y1; ty++) {
+        const float dy_lo = geo.py - (float)min(ty * LGR_TILE + LGR_TILE - 1, H - 1), dy_hi = geo.py - (float)(ty * LGR_TILE);
+        const float cy = fminf(fmaxf(0.f, dy_lo), dy_hi);
+        for (int tx = geo.rect.x0; tx < geo.rect.x1; tx++, b++) {
+            const float dx_lo = geo.px - (float)min(tx * LGR_TILE + LGR_TILE - 1, W - 1), dx_hi = geo.px - (float)(tx * LGR_TILE);
+            const float cx = fminf(fmaxf(0.f, dx_lo), dx_hi);
+            float q = 0.f;
+            if (cx != 0.f || cy != 0.f) {
+                q = 3.0e38f;
+                if (cx != 0.f) {
+                    const float dy = fminf(fmaxf(nbc * cx, dy_lo), dy_hi);
+                    q = hA * cx * cx + hC * dy * dy + B * cx * dy;
+                }
+                if (cy != 0.f) {
+                    const float dx = fminf(fmaxf(nba * cy, dx_lo), dx_hi);
+                    q = fminf(q, hA * dx * dx + hC * cy * cy + B * dx * cy);
+                }
+            }
+            if (!(q > thr)) m |= 1ull << b;
+        }
     }
-    kept = (uint32_t)__popcll(mask);
+    mask = m;
+    kept = (uint32_t)__popcll(m);
 }
 
 // ------------------------------------------------------------------------------------------------
