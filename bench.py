@@ -45,6 +45,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--dense-allreduce", action="store_true", help="N>1: all-reduce the dense gradients instead of the compact SH exchange")
     return ap.parse_args()
 
 
@@ -204,8 +205,12 @@ def main():
         for p in params:
             p.grad = None
 
+    fused_exchange = args.impl == "ours" and world > 1 and os.environ.get("LGR_FUSED", "1") != "0" and not args.dense_allreduce
+    if fused_exchange:
+        parallel.enable_gradient_exchange(world)   # gradients come out of backward() already summed over the ranks
+
     def allreduce_grads():  # the path's one exchange step: sum of the per-Gaussian gradients over the ranks (NCCL)
-        if world > 1:
+        if world > 1 and not fused_exchange:
             hs = [torch.distributed.all_reduce(p.grad, op=torch.distributed.ReduceOp.SUM, async_op=True) for p in params]
             for h in hs:
                 h.wait()
@@ -393,7 +398,9 @@ def main():
                                    "step = render()+L1+backward to raw leaves" + (" + 1 NCCL all-reduce of gradients" if world > 1 else ""),
                        "gaussians": P, "resolution": [W, H], "views_per_step": world, "parallelism": f"view-parallel x{world}",
                        "l2_policy": "inputs larger than L2 (>=0.7 GB of parameters streamed per step)",
-                       "grad_allreduce_bytes": grad_bytes if world > 1 else 0,
+                       "grad_exchange": ("none" if world == 1 else ("all-reduce 44 B/Gaussian + all-gather dRGB 12 B/Gaussian/rank, SH gradient rebuilt locally"
+                                                                    if fused_exchange else "dense all-reduce")),
+                       "grad_exchange_bytes_per_rank": 0 if world == 1 else (P * 44 + P * 12 * world if fused_exchange else grad_bytes),
                        "fused_activations": bool(args.impl == "ours" and os.environ.get("LGR_FUSED", "1") != "0")},
             "clocks": clocks, "gpu_launches": launches,
         }

@@ -118,6 +118,8 @@ typedef struct lgr_raw_grads { /* dL/d(leaf), same shapes, fully written */
     float* scaling;
     float* rotation;
     float* opacity;
+    float* rgb; /* optional [P,3]: clamp-masked dL/dRGB of this view.  When rgb != NULL and features_rest == NULL ("compact
+                   mode") features_dc / features_rest are not written: see lgr_sh_grad_from_views. */
 } lgr_raw_grads;
 
 /* gaussians_count / important_score may both be NULL (plain forward) or both non-NULL (significance mode). */
@@ -131,6 +133,14 @@ int lgr_forward_raw(const lgr_view* view, int P, int M, const lgr_raw_params* pa
 int lgr_backward_raw(const lgr_view* view, int P, int M, int num_rendered, const lgr_raw_params* params,
                      const int32_t* radii, char* geometry_blob, char* binning_blob, char* image_blob,
                      const float* dL_dout_color, const lgr_raw_grads* grads, float* dL_dmeans2D, void* cuda_stream);
+
+/* View-parallel training: for one view dL/dSH[k][c] = basis_k(dir) * dRGB[c] is rank-1 per Gaussian
+ * (RAST/cuda_rasterizer/backward.cu:44-97), so ranks exchange dRGB (12 B/Gaussian/view, all-gather) instead of the
+ * dense 12*M B/Gaussian gradient, and each rank rebuilds the SUM over views here:
+ *   d_features_dc/rest[i] = sum_v basis(normalize(xyz[i] - campos[v])) (x) d_rgb[v][i]       (rows k >= (D+1)^2 are zero)
+ * campos: [n_views,3] device; d_rgb: [n_views,P,3] device. */
+int lgr_sh_grad_from_views(int P, int M, int sh_degree, int n_views, const float* xyz, const float* campos, const float* d_rgb,
+                           float* d_features_dc, float* d_features_rest, void* cuda_stream);
 
 /* present[i] = (view-space z of point i) > 0.2   (RAST/cuda_rasterizer/rasterizer_impl.cu:54-66, auxiliary.h:139-164) */
 int lgr_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix, uint8_t* present,

@@ -33,6 +33,11 @@ class LgrRawParams(C.Structure):
                 ("rotation", C.c_void_p), ("opacity", C.c_void_p)]
 
 
+class LgrRawGrads(C.Structure):
+    """struct lgr_raw_grads: the six leaf gradients + the optional compact dL/dRGB factor"""
+    _fields_ = LgrRawParams._fields_ + [("rgb", C.c_void_p)]
+
+
 ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t)
 
 _lib = None
@@ -70,7 +75,9 @@ def load():
                                         vp, vp, vp, vp, C.POINTER(C.c_int32), vp]
         lib.lgr_backward_raw.restype = i32
         lib.lgr_backward_raw.argtypes = [C.POINTER(LgrView), i32, i32, i32, C.POINTER(LgrRawParams), vp, vp, vp, vp, vp,
-                                         C.POINTER(LgrRawParams), vp, vp]
+                                         C.POINTER(LgrRawGrads), vp, vp]
+        lib.lgr_sh_grad_from_views.restype = i32
+        lib.lgr_sh_grad_from_views.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]
         lib.lgr_mark_visible.restype = i32
         lib.lgr_mark_visible.argtypes = [i32, vp, vp, vp, vp, vp]
         lib.lgr_last_error.restype = C.c_char_p

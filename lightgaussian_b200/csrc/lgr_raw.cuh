@@ -219,6 +219,7 @@ struct RawBackArgs {
     float* d_rotation;
     float* d_opacity;
     float* dL_dmeans2D;
+    float* d_rgb;  // optional [P,3]: clamp-masked dL/dRGB (compact SH gradient factor); when set and d_rest == NULL the dense SH rows are not written
 };
 
 __global__ void __launch_bounds__(256) preprocess_backward_raw_kernel(RawBackArgs a)
@@ -317,7 +318,11 @@ __global__ void __launch_bounds__(256) preprocess_backward_raw_kernel(RawBackArg
         reinterpret_cast<float4*>(a.d_rotation)[si] = make_float4(dq[0], dq[1], dq[2], dq[3]);
         a.d_opacity[si] = dop;
         a.dL_dmeans2D[3 * si] = g2x; a.dL_dmeans2D[3 * si + 1] = g2y; a.dL_dmeans2D[3 * si + 2] = 0.f;
+        if (a.d_rgb) {
+            a.d_rgb[3 * si] = dRGB[0]; a.d_rgb[3 * si + 1] = dRGB[1]; a.d_rgb[3 * si + 2] = dRGB[2];
+        }
     }
+    if (a.d_rest == nullptr) return;  // compact mode: the SH gradient is rebuilt from d_rgb (sh_grad_from_views_kernel)
     __syncwarp();
     if (n == 32) {
         fence_async_smem();  // generic-proxy writes above -> visible to the bulk (async-proxy) store
@@ -327,6 +332,70 @@ __global__ void __launch_bounds__(256) preprocess_backward_raw_kernel(RawBackArg
             bulk_s2g(a.d_dc + (size_t)first * 3, s_dc, 384u);
             bulk_commit();
             bulk_wait_read_all();  // shared memory must stay valid until the copy engine has read it
+        }
+    } else {
+        for (int k = lane; k < n * nrest; k += 32) a.d_rest[(size_t)first * nrest + k] = s_rest[k];
+        for (int k = lane; k < n * 3; k += 32) a.d_dc[(size_t)first * 3 + k] = s_dc[k];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// View-parallel SH gradient.  For one view dL/dSH[k][c] = basis_k(dir) * dRGB[c] is rank-1 per Gaussian
+// (RAST/cuda_rasterizer/backward.cu:44-97), so ranks exchange the 3-float factor dRGB (all-gather, 12 B/Gaussian/view)
+// instead of all-reducing 12*M B/Gaussian, and every rank rebuilds  sum_v basis(dir_v) (x) dRGB_v  here.
+// dir_v = normalize(xyz - campos_v).  Rows are staged in shared memory and written with one bulk store per warp.
+// ------------------------------------------------------------------------------------------------------------------
+struct ShGradArgs {
+    int P, D, M, n_views;
+    const float* xyz;
+    const float* campos;  // [n_views,3]
+    const float* d_rgb;   // [n_views,P,3]
+    float* d_dc;          // [P,3]
+    float* d_rest;        // [P,(M-1)*3]
+};
+
+__global__ void __launch_bounds__(256) sh_grad_from_views_kernel(ShGradArgs a)
+{
+    extern __shared__ __align__(128) unsigned char dyn_smem[];
+    const int nrest = (a.M - 1) * 3;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* s_rest = reinterpret_cast<float*>(dyn_smem) + (size_t)warp * 32 * (nrest + 3);
+    float* s_dc = s_rest + 32 * nrest;
+    const int first = blockIdx.x * 256 + warp * 32;
+    if (first >= a.P) return;
+    const int n = min(32, a.P - first);
+    const int i = first + lane;
+    const size_t si = (size_t)i;
+    float* rr = s_rest + lane * nrest;
+    float* dd = s_dc + lane * 3;
+    if (lane < n) {
+        const float x = a.xyz[3 * si], y = a.xyz[3 * si + 1], z = a.xyz[3 * si + 2];
+        float acc[48];
+#pragma unroll
+        for (int k = 0; k < 48; k++) acc[k] = 0.f;
+        for (int v = 0; v < a.n_views; v++) {
+            const float* g = a.d_rgb + ((size_t)v * a.P + si) * 3;
+            const float dRGB[3] = {g[0], g[1], g[2]};
+            if (dRGB[0] == 0.f && dRGB[1] == 0.f && dRGB[2] == 0.f) continue;  // culled / fully clamped in this view
+            float unused[3] = {0.f, 0.f, 0.f};
+            const float cam[3] = {a.campos[3 * v], a.campos[3 * v + 1], a.campos[3 * v + 2]};
+            lgr::sh_backward(a.D, [&](int) { return 0.f; }, [&](int k, int c, float val) { acc[3 * k + c] += val; }, x, y, z, cam, dRGB,
+                             unused);
+        }
+        dd[0] = acc[0]; dd[1] = acc[1]; dd[2] = acc[2];
+#pragma unroll
+        for (int k = 3; k < 48; k++)
+            if (k - 3 < nrest) rr[k - 3] = acc[k];
+    }
+    __syncwarp();
+    if (n == 32) {
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+            bulk_s2g(a.d_rest + (size_t)first * nrest, s_rest, 128u * (uint32_t)nrest);
+            bulk_s2g(a.d_dc + (size_t)first * 3, s_dc, 384u);
+            bulk_commit();
+            bulk_wait_read_all();
         }
     } else {
         for (int k = lane; k < n * nrest; k += 32) a.d_rest[(size_t)first * nrest + k] = s_rest[k];

@@ -43,10 +43,10 @@ std::atomic<uint64_t> g_launches{0};
 
 // ---- optional per-stage device timing (CUDA events on the launch stream), used by bench.py's roofline ----
 enum StageId { ST_PREPROCESS = 0, ST_DEPTH_SORT, ST_SCAN, ST_EMIT, ST_TILE_SORT, ST_RANGES, ST_BLEND_FWD, ST_BLEND_FWD_COUNT,
-               ST_SCORE, ST_BLEND_BWD, ST_PREPROCESS_BWD, ST_MEMSET, ST_COUNT };
+               ST_SCORE, ST_BLEND_BWD, ST_PREPROCESS_BWD, ST_MEMSET, ST_SH_GRAD, ST_COUNT };
 const char* const kStageNames[ST_COUNT] = {"preprocess_kernel", "depth_sort(cub)", "scan(cub)", "emit_kernel", "tile_sort(cub)",
                                            "ranges_kernel", "blend_forward_kernel", "blend_forward_kernel<count>", "score_kernel",
-                                           "blend_backward_kernel", "preprocess_backward_kernel", "memset"};
+                                           "blend_backward_kernel", "preprocess_backward_kernel", "memset", "sh_grad_from_views_kernel"};
 struct ProfRecord { int stage; cudaEvent_t a, b; };
 bool g_prof_on = false;
 std::vector<ProfRecord> g_prof_records;
@@ -1275,9 +1275,10 @@ int lgr_backward_raw(const lgr_view* v, int P, int M, int num_rendered, const lg
 {
     cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
     if (P == 0) return LGR_OK;
+    const bool compact = grads && grads->rgb != nullptr && grads->features_rest == nullptr;
     if (!v || P < 0 || M < 1 || !params || !grads || !radii || !geometry_blob || !binning_blob || !image_blob || !dL_dout_color ||
-        !dL_dmeans2D || !grads->xyz || !grads->features_dc || (M > 1 && !grads->features_rest) || !grads->scaling || !grads->rotation ||
-        !grads->opacity) {
+        !dL_dmeans2D || !grads->xyz || (!compact && (!grads->features_dc || (M > 1 && !grads->features_rest))) || !grads->scaling ||
+        !grads->rotation || !grads->opacity) {
         g_last_error = "lgr_backward_raw: missing required argument";
         return LGR_ERR_INVALID_ARG;
     }
@@ -1313,6 +1314,8 @@ int lgr_backward_raw(const lgr_view* v, int P, int M, int num_rendered, const lg
     a.radii = radii; a.clamped = geo.clamped; a.acc = geo.grad_acc;
     a.d_xyz = grads->xyz; a.d_dc = grads->features_dc; a.d_rest = grads->features_rest; a.d_scaling = grads->scaling;
     a.d_rotation = grads->rotation; a.d_opacity = grads->opacity; a.dL_dmeans2D = dL_dmeans2D;
+    a.d_rgb = grads->rgb;
+    if (compact) { a.d_rest = nullptr; a.d_dc = nullptr; }
     const size_t smem = raw_smem_bytes(M);
     LGR_CUDA_TRY(cudaFuncSetAttribute(preprocess_backward_raw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     {
@@ -1320,6 +1323,27 @@ int lgr_backward_raw(const lgr_view* v, int P, int M, int num_rendered, const lg
         preprocess_backward_raw_kernel<<<(P + 255) / 256, 256, smem, stream>>>(a);
     }
     LGR_LAUNCH_CHECK("preprocess_backward_raw_kernel", debug, stream);
+    return LGR_OK;
+}
+
+int lgr_sh_grad_from_views(int P, int M, int sh_degree, int n_views, const float* xyz, const float* campos, const float* d_rgb,
+                           float* d_features_dc, float* d_features_rest, void* cuda_stream)
+{
+    if (P == 0 || n_views == 0) return LGR_OK;
+    if (P < 0 || M < 2 || M > 16 || sh_degree < 0 || sh_degree > 3 || (sh_degree + 1) * (sh_degree + 1) > M || !xyz || !campos || !d_rgb ||
+        !d_features_dc || !d_features_rest || ((uintptr_t)d_features_rest & 15) || ((uintptr_t)d_features_dc & 15)) {
+        g_last_error = "lgr_sh_grad_from_views: bad argument";
+        return LGR_ERR_INVALID_ARG;
+    }
+    cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+    ShGradArgs a{P, sh_degree, M, n_views, xyz, campos, d_rgb, d_features_dc, d_features_rest};
+    const size_t smem = raw_smem_bytes(M);
+    LGR_CUDA_TRY(cudaFuncSetAttribute(sh_grad_from_views_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {
+        ProfScope ps(ST_SH_GRAD, stream);
+        sh_grad_from_views_kernel<<<(P + 255) / 256, 256, smem, stream>>>(a);
+    }
+    LGR_LAUNCH_CHECK("sh_grad_from_views_kernel", false, stream);
     return LGR_OK;
 }
 

@@ -63,6 +63,15 @@ class FlatGrads:
         return self.flat.numel() * 4
 
 
+def enable_gradient_exchange(world: int, group=None):
+    """Training on `world` ranks: after this call the backward of render()'s fused node returns gradients already summed
+    over all ranks' views.  The four small leaves (44 B/Gaussian) go through ONE all-reduce; the SH gradient, which is
+    rank-1 per Gaussian and view, is exchanged as its 12 B/Gaussian factor (all-gather) and rebuilt locally
+    (lgr_sh_grad_from_views) -- about 4x less NVLink traffic than all-reducing the dense 12*M B/Gaussian tensor."""
+    from . import rasterizer
+    rasterizer.enable_gradient_exchange(world, group)
+
+
 def allreduce_counts(count: torch.Tensor, world: int) -> torch.Tensor:
     """exact, order-independent sum of per-Gaussian hit counts (int64)."""
     c = count.to(torch.int64)

@@ -81,3 +81,39 @@ def test_fused_count_render_equals_plain():
     np.testing.assert_array_equal(f["gaussians_count"], p["gaussians_count"])
     np.testing.assert_array_equal(f["important_score"], p["important_score"])
     assert f["gaussians_count"].sum() > 0
+
+
+def test_compact_sh_gradient_rebuild_matches_dense():
+    """lgr_backward_raw(compact) + lgr_sh_grad_from_views == dense SH gradients, for one view bit for bit and for the
+    sum of two views up to float summation order (the exchange used by view-parallel training)."""
+    from lightgaussian_b200 import rasterizer as R
+    W, H, P = 160, 120, 3000 + 17
+    scene = make_scene(P, sh_degree=3, seed=31, scale_mult=1.5)
+    pc = GaussianParams(scene["raw"], 3, "cuda", requires_grad=False)
+    leaves = (pc._xyz, pc._features_dc, pc._features_rest, pc._scaling, pc._rotation, pc._opacity)
+    bg = torch.zeros(3, device="cuda")
+    dense, rgbs, cams = [], [], []
+    for ci in (1, 3):
+        cam = TorchCamera(make_cameras(5, W, H)[ci], "cuda")
+        rs = R.GaussianRasterizationSettings(H, W, float(np.tan(cam.FoVx / 2)), float(np.tan(cam.FoVy / 2)), bg, 1.0, cam.world_view_transform,
+                                             cam.full_proj_transform, 3, cam.camera_center, False, False, False)
+        _, _, Rn, color, radii, geom, binning, img, lv = R._forward_raw_native(False, rs, *leaves)
+        dpix = torch.randn(3, H, W, generator=torch.Generator().manual_seed(ci)).cuda()
+        gd, _, _, _ = R.backward_raw_native(rs, Rn, dpix, *leaves, radii, geom, binning, img, compact=False)
+        gc, _, d_rgb, flat = R.backward_raw_native(rs, Rn, dpix, *leaves, radii, geom, binning, img, compact=True)
+        for a, b in ((gd[0], gc[0]), (gd[3], gc[3]), (gd[4], gc[4]), (gd[5], gc[5])):   # the small leaves are unaffected by the mode
+            assert rel_inf(b.cpu().numpy(), a.cpu().numpy()) <= 1e-3
+        d_dc1, d_rest1 = R.sh_grad_from_views(pc._xyz, cam.camera_center.reshape(1, 3), d_rgb.reshape(1, P, 3), pc._features_dc,
+                                              pc._features_rest, 3)
+        # same products, nothing to sum: identical up to the atomics' order inside dL/dRGB itself
+        assert rel_inf(d_rest1.cpu().numpy(), gd[2].cpu().numpy()) <= 1e-3
+        assert rel_inf(d_dc1.cpu().numpy(), gd[1].cpu().numpy()) <= 1e-3
+        dense.append(gd)
+        rgbs.append(d_rgb)
+        cams.append(cam.camera_center)
+    d_dc, d_rest = R.sh_grad_from_views(pc._xyz, torch.stack(cams), torch.stack(rgbs), pc._features_dc, pc._features_rest, 3)
+    ref_rest = (dense[0][2] + dense[1][2]).cpu().numpy()
+    ref_dc = (dense[0][1] + dense[1][1]).cpu().numpy()
+    assert np.abs(ref_rest).max() > 0
+    assert rel_inf(d_rest.cpu().numpy(), ref_rest) <= 1e-3 and rel_l2(d_rest.cpu().numpy(), ref_rest) <= 1e-4
+    assert rel_inf(d_dc.cpu().numpy(), ref_dc) <= 1e-3

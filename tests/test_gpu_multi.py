@@ -39,7 +39,15 @@ def _worker(rank, world, port, out):
     pkg["render"].sum().backward()
     flat.allreduce(world)
     torch.cuda.synchronize()
-    torch.save(dict(cnt=cnt.cpu(), imp=imp.cpu(), flat=flat.flat.cpu()), os.path.join(out, f"r{rank}.pt"))
+    # the same step with the compact exchange fused into backward()
+    parallel.enable_gradient_exchange(world)
+    for p in pc.parameters():
+        p.grad = None
+    render(cams[rank], pc, pipe, bg)["render"].sum().backward()
+    parallel.enable_gradient_exchange(1)
+    fused = torch.cat([p.grad.reshape(-1) for p in pc.parameters()])
+    torch.cuda.synchronize()
+    torch.save(dict(cnt=cnt.cpu(), imp=imp.cpu(), flat=flat.flat.cpu(), fused=fused.cpu()), os.path.join(out, f"r{rank}.pt"))
     torch.distributed.barrier()
     torch.distributed.destroy_process_group()
 
@@ -67,3 +75,5 @@ def test_two_gpu_results_equal_single_gpu(tmp_path):
         ref = grads[0] + grads[1]
         rel = (d["flat"] - ref).abs().max() / ref.abs().max()
         assert rel < 1e-3                               # backward atomics are order-dependent run to run
+        rel2 = (d["fused"] - ref).abs().max() / ref.abs().max()
+        assert rel2 < 1e-3                              # compact SH exchange == dense all-reduce
