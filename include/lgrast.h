@@ -134,6 +134,15 @@ int lgr_backward_raw(const lgr_view* view, int P, int M, int num_rendered, const
                      const int32_t* radii, char* geometry_blob, char* binning_blob, char* image_blob,
                      const float* dL_dout_color, const lgr_raw_grads* grads, float* dL_dmeans2D, void* cuda_stream);
 
+/* The same backward in two stages, so a caller can start exchanging this view's dL/dRGB (written to d_rgb[P,3] when non-NULL)
+ * while the per-Gaussian stage runs:  begin = accumulator clear + blend backward (+ dRGB extraction),  end = K7+K8.
+ * lgr_backward_raw == begin(d_rgb = NULL) followed by end.  In lgr_backward_raw_end, grads->features_rest == NULL selects the
+ * compact mode (SH leaves not written). */
+int lgr_backward_raw_begin(const lgr_view* view, int P, int num_rendered, const int32_t* radii, char* geometry_blob, char* binning_blob,
+                           char* image_blob, const float* dL_dout_color, float* d_rgb, void* cuda_stream);
+int lgr_backward_raw_end(const lgr_view* view, int P, int M, const lgr_raw_params* params, const int32_t* radii, char* geometry_blob,
+                         const lgr_raw_grads* grads, float* dL_dmeans2D, void* cuda_stream);
+
 /* View-parallel training: for one view dL/dSH[k][c] = basis_k(dir) * dRGB[c] is rank-1 per Gaussian
  * (RAST/cuda_rasterizer/backward.cu:44-97), so ranks exchange dRGB (12 B/Gaussian/view, all-gather) instead of the
  * dense 12*M B/Gaussian gradient, and each rank rebuilds the SUM over views here:

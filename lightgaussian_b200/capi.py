@@ -76,6 +76,10 @@ def load():
         lib.lgr_backward_raw.restype = i32
         lib.lgr_backward_raw.argtypes = [C.POINTER(LgrView), i32, i32, i32, C.POINTER(LgrRawParams), vp, vp, vp, vp, vp,
                                          C.POINTER(LgrRawGrads), vp, vp]
+        lib.lgr_backward_raw_begin.restype = i32
+        lib.lgr_backward_raw_begin.argtypes = [C.POINTER(LgrView), i32, i32, vp, vp, vp, vp, vp, vp, vp]
+        lib.lgr_backward_raw_end.restype = i32
+        lib.lgr_backward_raw_end.argtypes = [C.POINTER(LgrView), i32, i32, C.POINTER(LgrRawParams), vp, vp, C.POINTER(LgrRawGrads), vp, vp]
         lib.lgr_sh_grad_from_views.restype = i32
         lib.lgr_sh_grad_from_views.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]
         lib.lgr_mark_visible.restype = i32

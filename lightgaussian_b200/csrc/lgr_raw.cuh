@@ -403,6 +403,24 @@ __global__ void __launch_bounds__(256) sh_grad_from_views_kernel(ShGradArgs a)
     }
 }
 
+// dL/dRGB of this view straight from the blend-backward accumulators (clamp-masked, zero for culled Gaussians), so that the
+// all-gather of the compact SH factor can start BEFORE the per-Gaussian backward kernel runs.
+__global__ void __launch_bounds__(256) extract_drgb_kernel(int P, const int* __restrict__ radii, const uint8_t* __restrict__ clamped,
+                                                           const float* __restrict__ acc, float* __restrict__ d_rgb)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    float r = 0.f, g = 0.f, b = 0.f;
+    if (radii[i] > 0) {
+        const float4 r0 = *reinterpret_cast<const float4*>(acc + (size_t)i * ACC_STRIDE);
+        const unsigned cb = clamped[i];
+        r = (cb & 1u) ? 0.f : r0.x;
+        g = (cb & 2u) ? 0.f : r0.y;
+        b = (cb & 4u) ? 0.f : r0.z;
+    }
+    d_rgb[3 * (size_t)i] = r; d_rgb[3 * (size_t)i + 1] = g; d_rgb[3 * (size_t)i + 2] = b;
+}
+
 // important_score for the raw path: the activated opacity lives in conic_opacity.w (rows of culled Gaussians are unwritten)
 __global__ void __launch_bounds__(256) score_from_geom_kernel(int P, const int* __restrict__ count, const float4* __restrict__ conic_opacity,
                                                               float* __restrict__ score)

@@ -1269,22 +1269,14 @@ int lgr_forward_raw(const lgr_view* view, int P, int M, const lgr_raw_params* pa
                         num_rendered, cuda_stream, count_mode, params);
 }
 
-int lgr_backward_raw(const lgr_view* v, int P, int M, int num_rendered, const lgr_raw_params* params, const int32_t* radii,
-                     char* geometry_blob, char* binning_blob, char* image_blob, const float* dL_dout_color, const lgr_raw_grads* grads,
-                     float* dL_dmeans2D, void* cuda_stream)
+// stage 1 of the raw backward: clear the accumulators, blend backward, optionally extract this view's dL/dRGB
+int lgr_backward_raw_begin(const lgr_view* v, int P, int num_rendered, const int32_t* radii, char* geometry_blob, char* binning_blob,
+                           char* image_blob, const float* dL_dout_color, float* d_rgb, void* cuda_stream)
 {
     cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
     if (P == 0) return LGR_OK;
-    const bool compact = grads && grads->rgb != nullptr && grads->features_rest == nullptr;
-    if (!v || P < 0 || M < 1 || !params || !grads || !radii || !geometry_blob || !binning_blob || !image_blob || !dL_dout_color ||
-        !dL_dmeans2D || !grads->xyz || (!compact && (!grads->features_dc || (M > 1 && !grads->features_rest))) || !grads->scaling ||
-        !grads->rotation || !grads->opacity) {
-        g_last_error = "lgr_backward_raw: missing required argument";
-        return LGR_ERR_INVALID_ARG;
-    }
-    if (((uintptr_t)params->rotation & 15) || ((uintptr_t)grads->rotation & 15) || ((uintptr_t)params->features_rest & 15) ||
-        ((uintptr_t)params->features_dc & 15) || ((uintptr_t)grads->features_rest & 15) || ((uintptr_t)grads->features_dc & 15)) {
-        g_last_error = "lgr_backward_raw: rotation / features tensors and their gradients must be 16-byte aligned";
+    if (!v || P < 0 || !radii || !geometry_blob || !binning_blob || !image_blob || !dL_dout_color) {
+        g_last_error = "lgr_backward_raw_begin: missing required argument";
         return LGR_ERR_INVALID_ARG;
     }
     const bool debug = v->debug != 0;
@@ -1303,6 +1295,33 @@ int lgr_backward_raw(const lgr_view* v, int P, int M, int num_rendered, const lg
                                                             v->background, img.final_T, img.n_contrib, dL_dout_color, geo.grad_acc);
         LGR_LAUNCH_CHECK("blend_backward_kernel", debug, stream);
     }
+    if (d_rgb) {
+        extract_drgb_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, radii, geo.clamped, geo.grad_acc, d_rgb);
+        LGR_LAUNCH_CHECK("extract_drgb_kernel", debug, stream);
+    }
+    return LGR_OK;
+}
+
+// stage 2: the per-Gaussian backward (K7+K8 with the activation chain rules) from the accumulators left by stage 1
+int lgr_backward_raw_end(const lgr_view* v, int P, int M, const lgr_raw_params* params, const int32_t* radii, char* geometry_blob,
+                         const lgr_raw_grads* grads, float* dL_dmeans2D, void* cuda_stream)
+{
+    cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+    if (P == 0) return LGR_OK;
+    const bool compact = grads && grads->features_rest == nullptr;
+    if (!v || P < 0 || M < 1 || !params || !grads || !radii || !geometry_blob || !dL_dmeans2D || !grads->xyz ||
+        (!compact && (!grads->features_dc || (M > 1 && !grads->features_rest))) || !grads->scaling || !grads->rotation || !grads->opacity) {
+        g_last_error = "lgr_backward_raw: missing required argument";
+        return LGR_ERR_INVALID_ARG;
+    }
+    if (((uintptr_t)params->rotation & 15) || ((uintptr_t)grads->rotation & 15) || ((uintptr_t)params->features_rest & 15) ||
+        ((uintptr_t)params->features_dc & 15) || ((uintptr_t)grads->features_rest & 15) || ((uintptr_t)grads->features_dc & 15)) {
+        g_last_error = "lgr_backward_raw: rotation / features tensors and their gradients must be 16-byte aligned";
+        return LGR_ERR_INVALID_ARG;
+    }
+    const bool debug = v->debug != 0;
+    const int W = v->image_width, H = v->image_height;
+    GeometryState geo = carve_geometry(geometry_blob, (size_t)P);
     RawBackArgs a;
     a.P = P; a.D = v->sh_degree; a.M = M; a.W = W; a.H = H;
     a.fy = H / (2.0f * v->tan_fovy);
@@ -1324,6 +1343,15 @@ int lgr_backward_raw(const lgr_view* v, int P, int M, int num_rendered, const lg
     }
     LGR_LAUNCH_CHECK("preprocess_backward_raw_kernel", debug, stream);
     return LGR_OK;
+}
+
+int lgr_backward_raw(const lgr_view* v, int P, int M, int num_rendered, const lgr_raw_params* params, const int32_t* radii,
+                     char* geometry_blob, char* binning_blob, char* image_blob, const float* dL_dout_color, const lgr_raw_grads* grads,
+                     float* dL_dmeans2D, void* cuda_stream)
+{
+    const int st = lgr_backward_raw_begin(v, P, num_rendered, radii, geometry_blob, binning_blob, image_blob, dL_dout_color, nullptr, cuda_stream);
+    if (st != LGR_OK) return st;
+    return lgr_backward_raw_end(v, P, M, params, radii, geometry_blob, grads, dL_dmeans2D, cuda_stream);
 }
 
 int lgr_sh_grad_from_views(int P, int M, int sh_degree, int n_views, const float* xyz, const float* campos, const float* d_rgb,

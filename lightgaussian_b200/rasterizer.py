@@ -335,19 +335,64 @@ class _RasterizeRawLeaves(torch.autograd.Function):
         xyz, dc, rest, scaling, rotation, opacity, radii, geom, binning, img = ctx.saved_tensors
         world = _exchange["world"]
         exchange = world > 1 and xyz.size(0) != 0 and rest.size(1) > 0
-        g, g2d, d_rgb, flat = backward_raw_native(rs, ctx.num_rendered, grad_out_color, xyz, dc, rest, scaling, rotation, opacity, radii,
-                                                  geom, binning, img, compact=exchange)
-        if exchange:
-            import torch.distributed as dist
-            grp = _exchange["group"]
-            P = xyz.size(0)
-            all_rgb = torch.empty((world, P, 3), dtype=torch.float32, device=xyz.device)
-            all_cam = torch.empty((world, 3), dtype=torch.float32, device=xyz.device)
-            dist.all_gather_into_tensor(all_rgb, d_rgb, group=grp)
-            dist.all_gather_into_tensor(all_cam, rs.campos.reshape(1, 3).contiguous(), group=grp)
-            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=grp)
-            g[1], g[2] = sh_grad_from_views(xyz, all_cam, all_rgb, dc, rest, rs.sh_degree)
+        if not exchange:
+            g, g2d, _, _ = backward_raw_native(rs, ctx.num_rendered, grad_out_color, xyz, dc, rest, scaling, rotation, opacity, radii,
+                                               geom, binning, img, compact=False)
+        else:
+            g, g2d = _backward_raw_exchange(rs, ctx.num_rendered, grad_out_color, xyz, dc, rest, scaling, rotation, opacity, radii, geom,
+                                            binning, img, world, _exchange["group"])
         return g[0], g2d, g[1], g[2], g[3], g[4], g[5], None
+
+
+_side_streams = {}
+
+
+def _backward_raw_exchange(rs, num_rendered, grad_out_color, xyz, dc, rest, scaling, rotation, opacity, radii, geom, binning, img, world, grp):
+    """The view-parallel backward: every collective is issued as early as its input exists so that it overlaps kernels.
+
+        main stream :  blend backward + dRGB extract | K7+K8 (small leaves -> flat)            | wait
+        NCCL stream :                                | all-gather dRGB, campos | all-reduce flat |
+        side stream :                                                          | rebuild SH gradient from all views |
+    """
+    import torch.distributed as dist
+    lib = capi.load()
+    device = xyz.device
+    P, M = xyz.size(0), 1 + rest.size(1)
+    H, W = grad_out_color.size(1), grad_out_color.size(2)
+    g2d = torch.empty((P, 3), dtype=torch.float32, device=device)
+    flat = torch.empty(P * 11, dtype=torch.float32, device=device)   # rotation first: keeps it 16-byte aligned
+    g_rot, g_xyz = flat[:4 * P].view(P, 4), flat[4 * P:7 * P].view(P, 3)
+    g_scal, g_op = flat[7 * P:10 * P].view(P, 3), flat[10 * P:].view(P, 1)
+    d_rgb = torch.empty((P, 3), dtype=torch.float32, device=device)
+    all_rgb = torch.empty((world, P, 3), dtype=torch.float32, device=device)
+    all_cam = torch.empty((world, 3), dtype=torch.float32, device=device)
+    d_dc, d_rest = torch.empty_like(dc), torch.empty_like(rest)
+    dpix = _f32c(grad_out_color, "grad_out_color")
+    main = torch.cuda.current_stream(device)
+    side = _side_streams.setdefault(str(device), torch.cuda.Stream(device=device))
+    with torch.cuda.device(device):
+        view, keep = _make_view(device, rs.bg, rs.viewmatrix, rs.projmatrix, rs.campos, rs.tanfovx, rs.tanfovy, H, W, rs.scale_modifier,
+                                rs.sh_degree, False, rs.debug)
+        st = lib.lgr_backward_raw_begin(C.byref(view), P, int(num_rendered), radii.data_ptr(), geom.data_ptr(), binning.data_ptr(),
+                                        img.data_ptr(), dpix.data_ptr(), d_rgb.data_ptr(), main.cuda_stream)
+        capi.check(st, "lgr_backward_raw_begin")
+        w_rgb = dist.all_gather_into_tensor(all_rgb, d_rgb, group=grp, async_op=True)          # overlaps K7+K8 below
+        w_cam = dist.all_gather_into_tensor(all_cam, keep[3].reshape(1, 3), group=grp, async_op=True)
+        params = _raw_struct(xyz, dc, rest, scaling, rotation, opacity)
+        grads = _raw_grads_struct(g_xyz, None, None, g_scal, g_rot, g_op, rgb=None)
+        st = lib.lgr_backward_raw_end(C.byref(view), P, M, C.byref(params), radii.data_ptr(), geom.data_ptr(), C.byref(grads),
+                                      g2d.data_ptr(), main.cuda_stream)
+        capi.check(st, "lgr_backward_raw_end")
+        w_flat = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=grp, async_op=True)
+        with torch.cuda.stream(side):                                                            # overlaps the all-reduce
+            w_rgb.wait()
+            w_cam.wait()
+            st = lib.lgr_sh_grad_from_views(P, M, int(rs.sh_degree), world, xyz.data_ptr(), all_cam.data_ptr(), all_rgb.data_ptr(),
+                                            d_dc.data_ptr(), d_rest.data_ptr(), side.cuda_stream)
+            capi.check(st, "lgr_sh_grad_from_views")
+        w_flat.wait()
+        main.wait_stream(side)
+    return [g_xyz, d_dc, d_rest, g_scal, g_rot, g_op], g2d
 
 
 def backward_raw_native(rs, num_rendered, grad_out_color, xyz, dc, rest, scaling, rotation, opacity, radii, geom, binning, img,
