@@ -45,6 +45,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-exchange", action="store_true", help="DIAGNOSTIC ONLY (invalid for the metric): N>1 without any gradient exchange")
     ap.add_argument("--dense-allreduce", action="store_true", help="N>1: all-reduce the dense gradients instead of the compact SH exchange")
     return ap.parse_args()
 
@@ -205,12 +206,13 @@ def main():
         for p in params:
             p.grad = None
 
-    fused_exchange = args.impl == "ours" and world > 1 and os.environ.get("LGR_FUSED", "1") != "0" and not args.dense_allreduce
+    fused_exchange = (args.impl == "ours" and world > 1 and os.environ.get("LGR_FUSED", "1") != "0" and not args.dense_allreduce
+                      and not args.no_exchange)
     if fused_exchange:
         parallel.enable_gradient_exchange(world)   # gradients come out of backward() already summed over the ranks
 
     def allreduce_grads():  # the path's one exchange step: sum of the per-Gaussian gradients over the ranks (NCCL)
-        if world > 1 and not fused_exchange:
+        if world > 1 and not fused_exchange and not args.no_exchange:
             hs = [torch.distributed.all_reduce(p.grad, op=torch.distributed.ReduceOp.SUM, async_op=True) for p in params]
             for h in hs:
                 h.wait()
@@ -389,6 +391,8 @@ def main():
                                       "(oracle/_ref: forward.cu/backward.cu/rasterizer_impl.cu compiled unmodified for sm_100a) on the same GPU, "
                                       f"same steps; host has {os.cpu_count()} cores"}
 
+    if args.impl == "ours" and os.environ.get("LGR_EXCHANGE_TIMING", "0") == "1":
+        print(f"[rank {rank}] exchange timing: {rasterizer.exchange_timing_report()}", file=sys.stderr)
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -398,7 +402,7 @@ def main():
                                    "step = render()+L1+backward to raw leaves" + (" + 1 NCCL all-reduce of gradients" if world > 1 else ""),
                        "gaussians": P, "resolution": [W, H], "views_per_step": world, "parallelism": f"view-parallel x{world}",
                        "l2_policy": "inputs larger than L2 (>=0.7 GB of parameters streamed per step)",
-                       "grad_exchange": ("none" if world == 1 else ("all-reduce 44 B/Gaussian + all-gather dRGB 12 B/Gaussian/rank, SH gradient rebuilt locally"
+                       "grad_exchange": ("none" if world == 1 else "DISABLED (diagnostic run, not a valid measurement)" if args.no_exchange else ("all-reduce 44 B/Gaussian + all-gather dRGB 12 B/Gaussian/rank, SH gradient rebuilt locally"
                                                                     if fused_exchange else "dense all-reduce")),
                        "grad_exchange_bytes_per_rank": 0 if world == 1 else (P * 44 + P * 12 * world if fused_exchange else grad_bytes),
                        "fused_activations": bool(args.impl == "ours" and os.environ.get("LGR_FUSED", "1") != "0")},

@@ -345,6 +345,73 @@ class _RasterizeRawLeaves(torch.autograd.Function):
 
 
 _side_streams = {}
+_xtiming = {"on": __import__("os").environ.get("LGR_EXCHANGE_TIMING", "0") == "1", "rows": []}
+
+
+def exchange_timing_report():
+    """mean ms of (blend backward + extract, K7+K8, tail = exposed exchange) per exchange-mode backward (diagnostics)"""
+    rows = []
+    torch.cuda.synchronize()
+    for ev in _xtiming["rows"][5:]:
+        rows.append([ev[i].elapsed_time(ev[i + 1]) for i in range(3)])
+    if not rows:
+        return None
+    t = torch.tensor(rows).mean(dim=0).tolist()
+    return {"blend_bwd+extract_ms": t[0], "k8_ms": t[1], "exposed_exchange_ms": t[2], "n": len(rows)}
+
+
+class _SymmExchange:
+    """Persistent NVLink symmetric-memory buffers for the small-leaf all-reduce (torch.distributed._symmetric_memory).
+    With NVSwitch multicast the reduction happens IN the switch (multimem.ld_reduce / multimem.st, one pass over 44 B per
+    Gaussian) instead of NCCL's ring; falls back to the two-shot peer-memory kernel, and to NCCL if neither is usable.
+    Two buffers alternate so that the gradients returned by step k stay valid while step k+1 is being written."""
+
+    def __init__(self, device, P, world, group):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        grp = group if group is not None else dist.group.WORLD
+        self.group_name = grp.group_name
+        self.n = (P * 11 + 1023) // 1024 * 1024
+        self.bufs = [symm_mem.empty(self.n, dtype=torch.float32, device=device) for _ in range(2)]
+        self.hdls = [symm_mem.rendezvous(b, self.group_name) for b in self.bufs]
+        for b in self.bufs:
+            b.zero_()
+        self.multicast = all(int(getattr(h, "multicast_ptr", 0) or 0) != 0 for h in self.hdls)
+        self.turn = 0
+
+    def next(self):
+        self.turn ^= 1
+        return self.bufs[self.turn]
+
+    def all_reduce_(self, buf):
+        if self.multicast:
+            torch.ops.symm_mem.multimem_all_reduce_(buf, "sum", self.group_name)
+        else:
+            torch.ops.symm_mem.two_shot_all_reduce_(buf, "sum", self.group_name)
+
+
+_symm_cache = {}
+
+
+def _symm_exchange(device, P, world, group):
+    """collectively agreed: either every rank gets symmetric buffers or none does (then NCCL is used)"""
+    import os
+    import torch.distributed as dist
+    key = (str(device), P, world)
+    if key not in _symm_cache:
+        xb, ok = None, 1
+        if os.environ.get("LGR_SYMM_MEM", "1") == "0":
+            ok = 0
+        else:
+            try:
+                xb = _SymmExchange(device, P, world, group)
+            except Exception as ex:  # noqa: BLE001  (no multicast / no P2P / API drift: NCCL still works)
+                print(f"lightgaussian_b200: symmetric-memory all-reduce unavailable ({type(ex).__name__}: {ex}); using NCCL", flush=True)
+                ok = 0
+        flag = torch.tensor([ok], device=device, dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        _symm_cache[key] = xb if int(flag.item()) == 1 else None
+    return _symm_cache[key]
 
 
 def _backward_raw_exchange(rs, num_rendered, grad_out_color, xyz, dc, rest, scaling, rotation, opacity, radii, geom, binning, img, world, grp):
@@ -360,7 +427,9 @@ def _backward_raw_exchange(rs, num_rendered, grad_out_color, xyz, dc, rest, scal
     P, M = xyz.size(0), 1 + rest.size(1)
     H, W = grad_out_color.size(1), grad_out_color.size(2)
     g2d = torch.empty((P, 3), dtype=torch.float32, device=device)
-    flat = torch.empty(P * 11, dtype=torch.float32, device=device)   # rotation first: keeps it 16-byte aligned
+    xb = _symm_exchange(device, P, world, grp)
+    flat_full = xb.next() if xb is not None else torch.empty(P * 11, dtype=torch.float32, device=device)
+    flat = flat_full[:P * 11]                                         # rotation first: keeps it 16-byte aligned
     g_rot, g_xyz = flat[:4 * P].view(P, 4), flat[4 * P:7 * P].view(P, 3)
     g_scal, g_op = flat[7 * P:10 * P].view(P, 3), flat[10 * P:].view(P, 1)
     d_rgb = torch.empty((P, 3), dtype=torch.float32, device=device)
@@ -373,9 +442,14 @@ def _backward_raw_exchange(rs, num_rendered, grad_out_color, xyz, dc, rest, scal
     with torch.cuda.device(device):
         view, keep = _make_view(device, rs.bg, rs.viewmatrix, rs.projmatrix, rs.campos, rs.tanfovx, rs.tanfovy, H, W, rs.scale_modifier,
                                 rs.sh_degree, False, rs.debug)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if _xtiming["on"] else None
+        if ev:
+            ev[0].record(main)
         st = lib.lgr_backward_raw_begin(C.byref(view), P, int(num_rendered), radii.data_ptr(), geom.data_ptr(), binning.data_ptr(),
                                         img.data_ptr(), dpix.data_ptr(), d_rgb.data_ptr(), main.cuda_stream)
         capi.check(st, "lgr_backward_raw_begin")
+        if ev:
+            ev[1].record(main)
         w_rgb = dist.all_gather_into_tensor(all_rgb, d_rgb, group=grp, async_op=True)          # overlaps K7+K8 below
         w_cam = dist.all_gather_into_tensor(all_cam, keep[3].reshape(1, 3), group=grp, async_op=True)
         params = _raw_struct(xyz, dc, rest, scaling, rotation, opacity)
@@ -383,15 +457,23 @@ def _backward_raw_exchange(rs, num_rendered, grad_out_color, xyz, dc, rest, scal
         st = lib.lgr_backward_raw_end(C.byref(view), P, M, C.byref(params), radii.data_ptr(), geom.data_ptr(), C.byref(grads),
                                       g2d.data_ptr(), main.cuda_stream)
         capi.check(st, "lgr_backward_raw_end")
-        w_flat = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=grp, async_op=True)
+        if ev:
+            ev[2].record(main)
+        w_flat = None if xb is not None else dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=grp, async_op=True)
         with torch.cuda.stream(side):                                                            # overlaps the all-reduce
             w_rgb.wait()
             w_cam.wait()
             st = lib.lgr_sh_grad_from_views(P, M, int(rs.sh_degree), world, xyz.data_ptr(), all_cam.data_ptr(), all_rgb.data_ptr(),
                                             d_dc.data_ptr(), d_rest.data_ptr(), side.cuda_stream)
             capi.check(st, "lgr_sh_grad_from_views")
-        w_flat.wait()
+        if xb is not None:
+            xb.all_reduce_(flat_full)          # in-switch (NVLS multimem) or peer-memory two-shot reduction, on the main stream
+        else:
+            w_flat.wait()
         main.wait_stream(side)
+        if ev:
+            ev[3].record(main)
+            _xtiming["rows"].append(ev)
     return [g_xyz, d_dc, d_rest, g_scal, g_rot, g_op], g2d
 
 
