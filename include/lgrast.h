@@ -151,6 +151,13 @@ int lgr_backward_raw_end(const lgr_view* view, int P, int M, const lgr_raw_param
 int lgr_sh_grad_from_views(int P, int M, int sh_degree, int n_views, const float* xyz, const float* campos, const float* d_rgb,
                            float* d_features_dc, float* d_features_rest, void* cuda_stream);
 
+/* All-reduce (sum) of n_floats floats over NVLink peer memory, for the view-parallel gradient exchange.
+ * peer_buffers[r] (HOST array of `world` DEVICE pointers) is rank r's buffer as mapped into THIS process (symmetric /
+ * IPC memory, 16-byte aligned); n_floats must be a multiple of 4.  This rank reduces slice `rank` from all peers with P2P
+ * loads (fixed rank order: every rank obtains bit-identical sums) and stores it into all peers.  The caller must place a
+ * cross-GPU barrier on the stream BEFORE (all ranks' data written) and AFTER (all peers' stores landed) this call. */
+int lgr_peer_allreduce(float* const* peer_buffers, int rank, int world, size_t n_floats, void* cuda_stream);
+
 /* present[i] = (view-space z of point i) > 0.2   (RAST/cuda_rasterizer/rasterizer_impl.cu:54-66, auxiliary.h:139-164) */
 int lgr_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix, uint8_t* present,
                      void* cuda_stream);

@@ -421,6 +421,32 @@ __global__ void __launch_bounds__(256) extract_drgb_kernel(int P, const int* __r
     d_rgb[3 * (size_t)i] = r; d_rgb[3 * (size_t)i + 1] = g; d_rgb[3 * (size_t)i + 2] = b;
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// All-reduce (sum) over NVLink peer memory for the view-parallel gradient exchange.  Every rank holds a buffer of n floats
+// mapped into all peers (symmetric memory).  Rank r owns slice r: it loads that slice from ALL ranks with 128-bit P2P
+// loads, adds in rank order (so every rank computes bit-identical sums), and stores the result into ALL ranks' buffers.
+// Slice r of any buffer is read and written only by rank r, and each element is read before it is written by the same
+// thread, so one kernel between two cross-GPU barriers is enough (reduce-scatter + all-gather in one pass):
+// per GPU (N-1)/N * n floats in and out over NVLink, vs. 2x that through a ring.
+// ------------------------------------------------------------------------------------------------------------------
+struct PeerPtrs {
+    float* p[8];
+};
+
+__global__ void __launch_bounds__(512) peer_allreduce_kernel(PeerPtrs bufs, int rank, int world, size_t n_vec4)
+{
+    const size_t per = (n_vec4 + world - 1) / world;
+    const size_t lo = per * rank, hi = min(n_vec4, lo + per);
+    for (size_t i = lo + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (size_t)gridDim.x * blockDim.x) {
+        float4 acc = reinterpret_cast<const float4*>(bufs.p[0])[i];
+        for (int r = 1; r < world; r++) {
+            const float4 v = reinterpret_cast<const float4*>(bufs.p[r])[i];
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        for (int r = 0; r < world; r++) reinterpret_cast<float4*>(bufs.p[r])[i] = acc;
+    }
+}
+
 // important_score for the raw path: the activated opacity lives in conic_opacity.w (rows of culled Gaussians are unwritten)
 __global__ void __launch_bounds__(256) score_from_geom_kernel(int P, const int* __restrict__ count, const float4* __restrict__ conic_opacity,
                                                               float* __restrict__ score)

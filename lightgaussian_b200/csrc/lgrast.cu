@@ -43,10 +43,11 @@ std::atomic<uint64_t> g_launches{0};
 
 // ---- optional per-stage device timing (CUDA events on the launch stream), used by bench.py's roofline ----
 enum StageId { ST_PREPROCESS = 0, ST_DEPTH_SORT, ST_SCAN, ST_EMIT, ST_TILE_SORT, ST_RANGES, ST_BLEND_FWD, ST_BLEND_FWD_COUNT,
-               ST_SCORE, ST_BLEND_BWD, ST_PREPROCESS_BWD, ST_MEMSET, ST_SH_GRAD, ST_COUNT };
+               ST_SCORE, ST_BLEND_BWD, ST_PREPROCESS_BWD, ST_MEMSET, ST_SH_GRAD, ST_PEER_ALLREDUCE, ST_COUNT };
 const char* const kStageNames[ST_COUNT] = {"preprocess_kernel", "depth_sort(cub)", "scan(cub)", "emit_kernel", "tile_sort(cub)",
                                            "ranges_kernel", "blend_forward_kernel", "blend_forward_kernel<count>", "score_kernel",
-                                           "blend_backward_kernel", "preprocess_backward_kernel", "memset", "sh_grad_from_views_kernel"};
+                                           "blend_backward_kernel", "preprocess_backward_kernel", "memset", "sh_grad_from_views_kernel",
+                                           "peer_allreduce_kernel"};
 struct ProfRecord { int stage; cudaEvent_t a, b; };
 bool g_prof_on = false;
 std::vector<ProfRecord> g_prof_records;
@@ -1352,6 +1353,29 @@ int lgr_backward_raw(const lgr_view* v, int P, int M, int num_rendered, const lg
     const int st = lgr_backward_raw_begin(v, P, num_rendered, radii, geometry_blob, binning_blob, image_blob, dL_dout_color, nullptr, cuda_stream);
     if (st != LGR_OK) return st;
     return lgr_backward_raw_end(v, P, M, params, radii, geometry_blob, grads, dL_dmeans2D, cuda_stream);
+}
+
+int lgr_peer_allreduce(float* const* peer_buffers, int rank, int world, size_t n_floats, void* cuda_stream)
+{
+    if (world < 1 || world > 8 || rank < 0 || rank >= world || !peer_buffers || (n_floats & 3)) {
+        g_last_error = "lgr_peer_allreduce: need 1..8 ranks and a float count that is a multiple of 4";
+        return LGR_ERR_INVALID_ARG;
+    }
+    if (world == 1 || n_floats == 0) return LGR_OK;
+    PeerPtrs pp;
+    for (int r = 0; r < 8; r++) pp.p[r] = r < world ? peer_buffers[r] : nullptr;
+    for (int r = 0; r < world; r++)
+        if (!pp.p[r] || ((uintptr_t)pp.p[r] & 15)) {
+            g_last_error = "lgr_peer_allreduce: peer buffer missing or not 16-byte aligned";
+            return LGR_ERR_INVALID_ARG;
+        }
+    cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+    {
+        ProfScope ps(ST_PEER_ALLREDUCE, stream);
+        peer_allreduce_kernel<<<148 * 2, 512, 0, stream>>>(pp, rank, world, n_floats / 4);
+    }
+    LGR_LAUNCH_CHECK("peer_allreduce_kernel", false, stream);
+    return LGR_OK;
 }
 
 int lgr_sh_grad_from_views(int P, int M, int sh_degree, int n_views, const float* xyz, const float* campos, const float* d_rgb,

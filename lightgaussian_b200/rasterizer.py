@@ -361,10 +361,10 @@ def exchange_timing_report():
 
 
 class _SymmExchange:
-    """Persistent NVLink symmetric-memory buffers for the small-leaf all-reduce (torch.distributed._symmetric_memory).
-    With NVSwitch multicast the reduction happens IN the switch (multimem.ld_reduce / multimem.st, one pass over 44 B per
-    Gaussian) instead of NCCL's ring; falls back to the two-shot peer-memory kernel, and to NCCL if neither is usable.
-    Two buffers alternate so that the gradients returned by step k stay valid while step k+1 is being written."""
+    """Persistent NVLink symmetric-memory buffers (torch.distributed._symmetric_memory) for the small-leaf all-reduce,
+    reduced by OUR peer-memory kernel (lgr_peer_allreduce: P2P loads of this rank's slice from every peer, stores to every
+    peer) between two cross-GPU barriers.  Two buffers alternate so that the gradients returned by step k stay valid while
+    step k+1 is being written.  Any failure to set this up falls back to NCCL (agreed collectively in _symm_exchange)."""
 
     def __init__(self, device, P, world, group):
         import torch.distributed as dist
@@ -376,18 +376,27 @@ class _SymmExchange:
         self.hdls = [symm_mem.rendezvous(b, self.group_name) for b in self.bufs]
         for b in self.bufs:
             b.zero_()
-        self.multicast = all(int(getattr(h, "multicast_ptr", 0) or 0) != 0 for h in self.hdls)
+        self.rank, self.world = int(self.hdls[0].rank), int(self.hdls[0].world_size)
+        assert self.world == world
+        self.ptr_tables = []
+        for h in self.hdls:
+            ptrs = [int(p) for p in h.buffer_ptrs]
+            assert len(ptrs) == world and all(ptrs)
+            self.ptr_tables.append((C.c_void_p * world)(*ptrs))
         self.turn = 0
 
     def next(self):
         self.turn ^= 1
         return self.bufs[self.turn]
 
-    def all_reduce_(self, buf):
-        if self.multicast:
-            torch.ops.symm_mem.multimem_all_reduce_(buf, "sum", self.group_name)
-        else:
-            torch.ops.symm_mem.two_shot_all_reduce_(buf, "sum", self.group_name)
+    def all_reduce_(self, buf, stream):
+        k = self.turn
+        assert buf.data_ptr() == self.bufs[k].data_ptr()
+        h = self.hdls[k]
+        h.barrier(channel=0)      # every rank's K7+K8 has written its buffer
+        st = capi.load().lgr_peer_allreduce(self.ptr_tables[k], self.rank, self.world, self.n, stream.cuda_stream)
+        capi.check(st, "lgr_peer_allreduce")
+        h.barrier(channel=1)      # every peer's stores into this rank's buffer have landed
 
 
 _symm_cache = {}
@@ -400,13 +409,13 @@ def _symm_exchange(device, P, world, group):
     key = (str(device), P, world)
     if key not in _symm_cache:
         xb, ok = None, 1
-        if os.environ.get("LGR_SYMM_MEM", "1") == "0":
+        if os.environ.get("LGR_PEER_ALLREDUCE", "1") == "0":
             ok = 0
         else:
             try:
                 xb = _SymmExchange(device, P, world, group)
             except Exception as ex:  # noqa: BLE001  (no multicast / no P2P / API drift: NCCL still works)
-                print(f"lightgaussian_b200: symmetric-memory all-reduce unavailable ({type(ex).__name__}: {ex}); using NCCL", flush=True)
+                print(f"lightgaussian_b200: peer-memory all-reduce unavailable ({type(ex).__name__}: {ex}); using NCCL", flush=True)
                 ok = 0
         flag = torch.tensor([ok], device=device, dtype=torch.int32)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
@@ -467,7 +476,7 @@ def _backward_raw_exchange(rs, num_rendered, grad_out_color, xyz, dc, rest, scal
                                             d_dc.data_ptr(), d_rest.data_ptr(), side.cuda_stream)
             capi.check(st, "lgr_sh_grad_from_views")
         if xb is not None:
-            xb.all_reduce_(flat_full)          # in-switch (NVLS multimem) or peer-memory two-shot reduction, on the main stream
+            xb.all_reduce_(flat_full, main)    # our peer-memory reduction over NVLink, on the main stream
         else:
             w_flat.wait()
         main.wait_stream(side)
