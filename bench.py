@@ -334,7 +334,7 @@ def main():
 
     # ---------------- roofline of the dominant kernel (rank 0, our arm) ----------------
     roofline, stages = None, None
-    if args.impl == "ours" and not args.no_roofline and rank == 0:
+    if args.impl == "ours" and not args.no_roofline:   # every rank takes part (the backward contains collectives when N > 1)
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(peaks_path):
             peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
@@ -353,6 +353,7 @@ def main():
             Rs.append(int(rasterizer.last_num_rendered()))
         prof = capi.profile_collect()
         capi.profile_enable(False)
+        barrier()
         Pv, R, N, M = float(np.mean(vis)), float(np.mean(Rs)), W * H, 16
         # ALGORITHMIC bytes per launch (split per kernel in DESIGN.md section 4)
         alg = {
@@ -363,6 +364,8 @@ def main():
             "blend_backward_kernel": 20 * N + 40 * R + 44 * Pv,
             "preprocess_backward_kernel": 44 * Pv + 12 * P + Pv * (32 + 12 * M) + P * (56 + 12 * M),
             "memset": 48 * P,
+            "sh_grad_from_views_kernel": 12 * P + 12 * P * world + 12 * M * P,
+            "peer_allreduce_kernel": 2 * 44 * P * (world - 1) / max(world, 1),
         }
         stages = {k: {"ms_per_launch": ms_k / n, "launches": n, "alg_bytes": alg.get(k),
                       "gbs": (alg[k] / (ms_k / n * 1e-3) / 1e9) if k in alg else None}
