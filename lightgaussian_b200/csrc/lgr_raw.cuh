@@ -437,13 +437,34 @@ __global__ void __launch_bounds__(512) peer_allreduce_kernel(PeerPtrs bufs, int 
 {
     const size_t per = (n_vec4 + world - 1) / world;
     const size_t lo = per * rank, hi = min(n_vec4, lo + per);
-    for (size_t i = lo + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (size_t)gridDim.x * blockDim.x) {
-        float4 acc = reinterpret_cast<const float4*>(bufs.p[0])[i];
-        for (int r = 1; r < world; r++) {
-            const float4 v = reinterpret_cast<const float4*>(bufs.p[r])[i];
-            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    constexpr int U = 4;  // independent 128-bit peer loads in flight per thread and peer (NVLink latency ~2 us)
+    for (size_t base = lo + (size_t)blockIdx.x * blockDim.x + threadIdx.x; base < hi; base += stride * U) {
+        float4 acc[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const size_t i = base + u * stride;
+            acc[u] = i < hi ? reinterpret_cast<const float4*>(bufs.p[0])[i] : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        for (int r = 0; r < world; r++) reinterpret_cast<float4*>(bufs.p[r])[i] = acc;
+        for (int r = 1; r < world; r++) {
+            float4 v[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const size_t i = base + u * stride;
+                v[u] = i < hi ? reinterpret_cast<const float4*>(bufs.p[r])[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                acc[u].x += v[u].x; acc[u].y += v[u].y; acc[u].z += v[u].z; acc[u].w += v[u].w;
+            }
+        }
+        for (int r = 0; r < world; r++) {
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const size_t i = base + u * stride;
+                if (i < hi) reinterpret_cast<float4*>(bufs.p[r])[i] = acc[u];
+            }
+        }
     }
 }
 
