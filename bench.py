@@ -375,12 +375,30 @@ def main():
         tot_ms = sum(v["ms_per_launch"] * v["launches"] for v in stages.values()) / nprof
         Bf = 12 * P + Pv * (32 + 12 * M) + 4 * P + 40 * Pv + 28 * R + 40 * R + 20 * N
         Bb = 20 * N + 40 * R + 88 * Pv + 12 * P + Pv * (32 + 12 * M) + P * (56 + 12 * M)
+        traffic = None   # DRAM bytes per launch of this kernel from the committed ncu --set full capture of the same workload
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tpath) and (P, W, H) == (3_000_000, 1920, 1080):
+            for kname, bytes_ in json.load(open(tpath))["dram_bytes_per_launch"].items():
+                if kname.split("<")[0].replace("_raw", "") == top.replace("_raw", ""):
+                    traffic = bytes_
         roofline = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": None, "peak_source": peak_src,
+                    "traffic": traffic, "peak_source": peak_src,
                     "share_of_native_time": stages[top]["ms_per_launch"] * stages[top]["launches"] / nprof / tot_ms,
                     "whole_view": {"alg_bytes": Bf + Bb, "native_ms_per_view": tot_ms,
                                    "achieved": (Bf + Bb) / (tot_ms * 1e-3) / 1e9, "frac": (Bf + Bb) / (tot_ms * 1e-3) / 1e9 / peak},
                     "measured": {"P_visible": Pv, "num_rendered": R}}
+
+    # ---------------- significance pass (prune.prune_list): count_render over this rank's cameras ----------------
+    signif = None
+    if args.impl == "ours" and not args.no_roofline:
+        from lightgaussian_b200.renderer import count_render
+        with torch.no_grad():
+            for i in range(3):
+                count_render(cams[i], pc, pipe, bg)
+            nsig = min(len(cams), 16)
+            t_sig, _ = timed(lambda s: count_render(cams[(s * world + rank) % len(cams)], pc, pipe, bg), nsig)
+        signif = {"value": nsig * world / (t_sig * 1e-3), "unit": "views/s", "views": nsig * world,
+                  "what": "count_render() (forward + exact Global Significance counts), cameras sharded over ranks"}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -421,6 +439,8 @@ def main():
         if roofline:
             line["roofline"] = roofline
             line["stages"] = stages
+        if signif:
+            line["significance_pass"] = signif
         if cpu_baseline:
             line["cpu_baseline"] = cpu_baseline
         print(json.dumps(line))
