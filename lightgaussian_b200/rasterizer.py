@@ -345,6 +345,7 @@ class _RasterizeRawLeaves(torch.autograd.Function):
 
 
 _side_streams = {}
+_hp_streams = {}
 _xtiming = {"on": __import__("os").environ.get("LGR_EXCHANGE_TIMING", "0") == "1", "rows": []}
 
 
@@ -468,7 +469,16 @@ def _backward_raw_exchange(rs, num_rendered, grad_out_color, xyz, dc, rest, scal
         capi.check(st, "lgr_backward_raw_end")
         if ev:
             ev[2].record(main)
-        w_flat = None if xb is not None else dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=grp, async_op=True)
+        # critical path first: the small-leaf reduction runs on a HIGH-priority stream so that its blocks are scheduled ahead
+        # of the bandwidth-hungry rebuild kernel that overlaps it
+        if xb is not None:
+            hp = _hp_streams.setdefault(str(device), torch.cuda.Stream(device=device, priority=-1))
+            hp.wait_stream(main)
+            with torch.cuda.stream(hp):
+                xb.all_reduce_(flat_full, hp)  # our peer-memory reduction over NVLink
+            w_flat = None
+        else:
+            w_flat = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=grp, async_op=True)
         with torch.cuda.stream(side):                                                            # overlaps the all-reduce
             w_rgb.wait()
             w_cam.wait()
@@ -476,7 +486,7 @@ def _backward_raw_exchange(rs, num_rendered, grad_out_color, xyz, dc, rest, scal
                                             d_dc.data_ptr(), d_rest.data_ptr(), side.cuda_stream)
             capi.check(st, "lgr_sh_grad_from_views")
         if xb is not None:
-            xb.all_reduce_(flat_full, main)    # our peer-memory reduction over NVLink, on the main stream
+            main.wait_stream(hp)
         else:
             w_flat.wait()
         main.wait_stream(side)
