@@ -107,62 +107,7 @@ __device__ __forceinline__ bool warp_stage_sh_begin(const float* __restrict__ re
     return bulk;
 }
 
-// K1 of the fused path is split in two so that the bandwidth-heavy half overlaps the latency-bound binning chain:
-//   preprocess_raw_geom_kernel   xyz / scaling / rotation / opacity -> cull, cov3D, EWA projection, tile rectangle + keep-mask,
-//                                depth key.  Everything the depth sort / scan / emit / tile sort need (~25 % of K1's bytes).
-//   preprocess_raw_color_kernel  SH rows (TMA bulk-staged per warp) -> view-dependent RGB + clamp bits, only read by the
-//                                blend.  Launched on the library's auxiliary stream; the blend waits on its event.
-__global__ void __launch_bounds__(256) preprocess_raw_geom_kernel(RawArgs a, int* __restrict__ radii, GeometryState g)
-{
-    __shared__ float s_cam[36];
-    if (threadIdx.x < 16) s_cam[threadIdx.x] = a.view[threadIdx.x];
-    else if (threadIdx.x < 32) s_cam[threadIdx.x] = a.proj[threadIdx.x - 16];
-    else if (threadIdx.x < 35) s_cam[threadIdx.x] = a.campos[threadIdx.x - 32];
-    __syncthreads();
-    const float* view = s_cam;
-    const float* proj = s_cam + 16;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.P) return;
-    const float x = a.xyz[3 * (size_t)i], y = a.xyz[3 * (size_t)i + 1], z = a.xyz[3 * (size_t)i + 2];
-    lgr::Geom geo;
-    bool visible = lgr::xform_row(view, 2, x, y, z) > 0.2f;
-    if (visible) {
-        const float s0 = act_exp(a.scaling[3 * (size_t)i]), s1 = act_exp(a.scaling[3 * (size_t)i + 1]), s2 = act_exp(a.scaling[3 * (size_t)i + 2]);
-        float dn, cov[6];
-        const float4 q = act_normalize(reinterpret_cast<const float4*>(a.rotation)[i], dn);
-        lgr::cov3d_from_scale_rot(s0, s1, s2, a.mod, q.x, q.y, q.z, q.w, cov);
-#pragma unroll
-        for (int k = 0; k < 6; k++) g.cov3D[6 * (size_t)i + k] = cov[k];
-        visible = lgr::project_gaussian(x, y, z, view, proj, cov, a.fx, a.fy, a.tanx, a.tany, a.W, a.H, a.gx, a.gy, geo);
-    } else if (a.prefiltered) {
-        printf("Point is filtered although prefiltered is set. This shouldn't happen!");
-        __trap();
-    }
-    g.iota[i] = (uint32_t)i;
-    if (!visible) {
-        radii[i] = 0;
-        g.tiles_touched[i] = 0;
-        g.tiles_kept[i] = 0;
-        g.depth_keys[i] = 0xffffffffu;
-        g.clamped[i] = 0;
-        return;
-    }
-    radii[i] = geo.radius;
-    g.depth[i] = geo.depth;
-    g.depth_keys[i] = __float_as_uint(geo.depth);
-    g.means2D[i] = make_float2(geo.px, geo.py);
-    const float4 co = make_float4(geo.conic_x, geo.conic_y, geo.conic_z, act_sigmoid(a.opacity[i]));
-    g.conic_opacity[i] = co;
-    const uint32_t area = (uint32_t)((geo.rect.y1 - geo.rect.y0) * (geo.rect.x1 - geo.rect.x0));
-    g.tiles_touched[i] = area;
-    unsigned long long mask;
-    uint32_t kept;
-    tile_keep_mask(geo, co, a.W, a.H, mask, kept);
-    g.tiles_kept[i] = kept;
-    g.keep_mask[i] = mask;
-}
-
-__global__ void __launch_bounds__(256) preprocess_raw_color_kernel(RawArgs a, const int* __restrict__ radii, GeometryState g)
+__global__ void __launch_bounds__(256) preprocess_raw_kernel(RawArgs a, int* __restrict__ radii, GeometryState g)
 {
     extern __shared__ __align__(128) unsigned char dyn_smem[];
     const int nrest = (a.M - 1) * 3;
@@ -171,24 +116,73 @@ __global__ void __launch_bounds__(256) preprocess_raw_color_kernel(RawArgs a, co
     float* s_dc = s_rest + 32 * nrest;
     uint64_t* bars = reinterpret_cast<uint64_t*>(dyn_smem + (size_t)8 * 128 * (nrest + 3));
     float* s_cam = reinterpret_cast<float*>(bars + 8);
-    if (threadIdx.x < 3) s_cam[threadIdx.x] = a.campos[threadIdx.x];
+    if (threadIdx.x < 16) s_cam[threadIdx.x] = a.view[threadIdx.x];
+    else if (threadIdx.x < 32) s_cam[threadIdx.x] = a.proj[threadIdx.x - 16];
+    else if (threadIdx.x < 35) s_cam[threadIdx.x] = a.campos[threadIdx.x - 32];
     if (lane == 0) {
         mbar_init(&bars[warp], 1);
         fence_mbar_init();
     }
     __syncthreads();
-    const float* cam = s_cam;
+    const float* view = s_cam;
+    const float* proj = s_cam + 16;
+    const float* cam = s_cam + 32;
+
     const int first = blockIdx.x * 256 + warp * 32;
     if (first >= a.P) return;
     const int n = min(32, a.P - first);
     const int i = first + lane;
-    const bool visible = lane < n && radii[i] > 0;
-    if (!__any_sync(FULL, visible)) return;
-    const bool bulk = warp_stage_sh_begin(a.rest, a.dc, nrest, first, n, s_rest, s_dc, &bars[warp], lane);
-    float x = 0.f, y = 0.f, z = 0.f;
-    if (visible) {
+    const bool valid = lane < n;
+
+    float x = 0.f, y = 0.f, z = 0.f, cov[6];
+    lgr::Geom geo;
+    bool visible = false;
+    if (valid) {
         x = a.xyz[3 * (size_t)i]; y = a.xyz[3 * (size_t)i + 1]; z = a.xyz[3 * (size_t)i + 2];
+        visible = lgr::xform_row(view, 2, x, y, z) > 0.2f;
+        if (visible) {
+            const float s0 = act_exp(a.scaling[3 * (size_t)i]), s1 = act_exp(a.scaling[3 * (size_t)i + 1]), s2 = act_exp(a.scaling[3 * (size_t)i + 2]);
+            float dn;
+            const float4 q = act_normalize(reinterpret_cast<const float4*>(a.rotation)[i], dn);
+            lgr::cov3d_from_scale_rot(s0, s1, s2, a.mod, q.x, q.y, q.z, q.w, cov);
+#pragma unroll
+            for (int k = 0; k < 6; k++) g.cov3D[6 * (size_t)i + k] = cov[k];
+            visible = lgr::project_gaussian(x, y, z, view, proj, cov, a.fx, a.fy, a.tanx, a.tany, a.W, a.H, a.gx, a.gy, geo);
+        } else if (a.prefiltered) {
+            printf("Point is filtered although prefiltered is set. This shouldn't happen!");
+            __trap();
+        }
     }
+    const bool any_vis = __any_sync(FULL, visible);
+    bool bulk = false;
+    if (any_vis) bulk = warp_stage_sh_begin(a.rest, a.dc, nrest, first, n, s_rest, s_dc, &bars[warp], lane);
+
+    // everything that does not need the SH rows overlaps the copy
+    if (valid) {
+        g.iota[i] = (uint32_t)i;
+        if (!visible) {
+            radii[i] = 0;
+            g.tiles_touched[i] = 0;
+            g.tiles_kept[i] = 0;
+            g.depth_keys[i] = 0xffffffffu;
+            g.clamped[i] = 0;
+        } else {
+            radii[i] = geo.radius;
+            g.depth[i] = geo.depth;
+            g.depth_keys[i] = __float_as_uint(geo.depth);
+            g.means2D[i] = make_float2(geo.px, geo.py);
+            const float4 co = make_float4(geo.conic_x, geo.conic_y, geo.conic_z, act_sigmoid(a.opacity[i]));
+            g.conic_opacity[i] = co;
+            const uint32_t area = (uint32_t)((geo.rect.y1 - geo.rect.y0) * (geo.rect.x1 - geo.rect.x0));
+            g.tiles_touched[i] = area;
+            unsigned long long mask;
+            uint32_t kept;
+            tile_keep_mask(geo, co, a.W, a.H, mask, kept);
+            g.tiles_kept[i] = kept;
+            g.keep_mask[i] = mask;
+        }
+    }
+    if (!any_vis) return;
     if (bulk) mbar_wait(&bars[warp], 0);
     else __syncwarp();
     if (visible) {

@@ -43,11 +43,11 @@ std::atomic<uint64_t> g_launches{0};
 
 // ---- optional per-stage device timing (CUDA events on the launch stream), used by bench.py's roofline ----
 enum StageId { ST_PREPROCESS = 0, ST_DEPTH_SORT, ST_SCAN, ST_EMIT, ST_TILE_SORT, ST_RANGES, ST_BLEND_FWD, ST_BLEND_FWD_COUNT,
-               ST_SCORE, ST_BLEND_BWD, ST_PREPROCESS_BWD, ST_MEMSET, ST_SH_GRAD, ST_PEER_ALLREDUCE, ST_PREPROCESS_COLOR, ST_COUNT };
+               ST_SCORE, ST_BLEND_BWD, ST_PREPROCESS_BWD, ST_MEMSET, ST_SH_GRAD, ST_PEER_ALLREDUCE, ST_COUNT };
 const char* const kStageNames[ST_COUNT] = {"preprocess_kernel", "depth_sort(cub)", "scan(cub)", "emit_kernel", "tile_sort(cub)",
                                            "ranges_kernel", "blend_forward_kernel", "blend_forward_kernel<count>", "score_kernel",
                                            "blend_backward_kernel", "preprocess_backward_kernel", "memset", "sh_grad_from_views_kernel",
-                                           "peer_allreduce_kernel", "preprocess_color_kernel(aux stream)"};
+                                           "peer_allreduce_kernel"};
 struct ProfRecord { int stage; cudaEvent_t a, b; };
 bool g_prof_on = false;
 std::vector<ProfRecord> g_prof_records;
@@ -928,34 +928,6 @@ struct PinnedInt {
 };
 thread_local PinnedInt t_pinned;
 
-// One auxiliary stream + two events per device, owned by the library: the colour half of the fused preprocess runs there,
-// overlapping the latency-bound binning chain on the caller's stream.
-struct AuxStream {
-    cudaStream_t stream = nullptr;
-    cudaEvent_t fork = nullptr, join = nullptr;
-};
-std::mutex g_aux_mutex;
-AuxStream g_aux[64];
-
-int aux_for_current_device(AuxStream** out)
-{
-    int dev = 0;
-    LGR_CUDA_TRY(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 64) {
-        g_last_error = "device index out of range";
-        return LGR_ERR_INVALID_ARG;
-    }
-    std::lock_guard<std::mutex> l(g_aux_mutex);
-    AuxStream& a = g_aux[dev];
-    if (!a.stream) {
-        LGR_CUDA_TRY(cudaStreamCreateWithFlags(&a.stream, cudaStreamNonBlocking));
-        LGR_CUDA_TRY(cudaEventCreateWithFlags(&a.fork, cudaEventDisableTiming));
-        LGR_CUDA_TRY(cudaEventCreateWithFlags(&a.join, cudaEventDisableTiming));
-    }
-    *out = &a;
-    return LGR_OK;
-}
-
 int forward_impl(const lgr_view* v, int P, int M, const float* means3D, const float* shs, const float* colors_precomp,
                  const float* opacities, const float* scales, const float* rotations, const float* cov3D_precomp,
                  lgr_alloc_fn geometry_alloc, void* geometry_user, lgr_alloc_fn binning_alloc, void* binning_user,
@@ -1027,7 +999,6 @@ int forward_impl(const lgr_view* v, int P, int M, const float* means3D, const fl
 
     int R = 0, R_ref = 0;
     BinningState bin;
-    AuxStream* aux = nullptr;
     if (P > 0) {
         PreprocessArgs a;
         a.P = P; a.D = v->sh_degree; a.M = M; a.W = W; a.H = H; a.gx = gx; a.gy = gy;
@@ -1045,28 +1016,15 @@ int forward_impl(const lgr_view* v, int P, int M, const float* means3D, const fl
             ra.xyz = raw->xyz; ra.dc = raw->features_dc; ra.rest = raw->features_rest; ra.scaling = raw->scaling;
             ra.rotation = raw->rotation; ra.opacity = raw->opacity; ra.view = a.view; ra.proj = a.proj; ra.campos = a.campos;
             ra.prefiltered = a.prefiltered;
-            {
-                ProfScope ps(ST_PREPROCESS, stream);
-                preprocess_raw_geom_kernel<<<blocks, 256, 0, stream>>>(ra, radii, geo);
-            }
-            LGR_LAUNCH_CHECK("preprocess_raw_geom_kernel", debug, stream);
-            // colour half on the auxiliary stream: needs the geometry kernel's radii; joined before the blend
-            const int ast = aux_for_current_device(&aux);
-            if (ast != LGR_OK) return ast;
             const size_t smem = raw_smem_bytes(M);
-            LGR_CUDA_TRY(cudaFuncSetAttribute(preprocess_raw_color_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            LGR_CUDA_TRY(cudaEventRecord(aux->fork, stream));
-            LGR_CUDA_TRY(cudaStreamWaitEvent(aux->stream, aux->fork, 0));
-            {
-                ProfScope ps(ST_PREPROCESS_COLOR, aux->stream);
-                preprocess_raw_color_kernel<<<blocks, 256, smem, aux->stream>>>(ra, radii, geo);
-            }
-            LGR_CUDA_TRY(cudaEventRecord(aux->join, aux->stream));
+            LGR_CUDA_TRY(cudaFuncSetAttribute(preprocess_raw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ProfScope ps(ST_PREPROCESS, stream);
+            preprocess_raw_kernel<<<blocks, 256, smem, stream>>>(ra, radii, geo);
         } else {
             ProfScope ps(ST_PREPROCESS, stream);
             preprocess_kernel<<<blocks, 256, 0, stream>>>(a, radii, geo);
         }
-        if (!raw) LGR_LAUNCH_CHECK("preprocess_kernel", debug, stream);
+        LGR_LAUNCH_CHECK("preprocess_kernel", debug, stream);
 
         size_t tmp = geo.cub_temp_bytes;
         {
@@ -1130,10 +1088,6 @@ int forward_impl(const lgr_view* v, int P, int M, const float* means3D, const fl
         LGR_LAUNCH_CHECK("ranges_kernel", debug, stream);
     }
     if (count_mode && P > 0) LGR_CUDA_TRY(cudaMemsetAsync(gaussians_count, 0, sizeof(int) * (size_t)P, stream));
-    if (aux) {  // the colours must be there before the blend
-        LGR_CUDA_TRY(cudaStreamWaitEvent(stream, aux->join, 0));
-        LGR_LAUNCH_CHECK("preprocess_raw_color_kernel", debug, stream);
-    }
     {
         const int tiles = gx * gy;
         ProfScope ps(count_mode ? ST_BLEND_FWD_COUNT : ST_BLEND_FWD, stream);
