@@ -158,6 +158,10 @@ int lgr_sh_grad_from_views(int P, int M, int sh_degree, int n_views, const float
  * cross-GPU barrier on the stream BEFORE (all ranks' data written) and AFTER (all peers' stores landed) this call. */
 int lgr_peer_allreduce(float* const* peer_buffers, int rank, int world, size_t n_floats, void* cuda_stream);
 
+/* Same contract as lgr_peer_allreduce, with the sum formed inside the NVSwitch: multicast_ptr is the NVLS multicast mapping
+ * of the symmetric buffer (multimem.ld_reduce / multimem.st).  Barriers before and after are the caller's. */
+int lgr_multimem_allreduce(float* multicast_ptr, int rank, int world, size_t n_floats, void* cuda_stream);
+
 /* present[i] = (view-space z of point i) > 0.2   (RAST/cuda_rasterizer/rasterizer_impl.cu:54-66, auxiliary.h:139-164) */
 int lgr_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix, uint8_t* present,
                      void* cuda_stream);

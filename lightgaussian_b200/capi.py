@@ -82,6 +82,8 @@ def load():
         lib.lgr_backward_raw_end.argtypes = [C.POINTER(LgrView), i32, i32, C.POINTER(LgrRawParams), vp, vp, C.POINTER(LgrRawGrads), vp, vp]
         lib.lgr_peer_allreduce.restype = i32
         lib.lgr_peer_allreduce.argtypes = [C.POINTER(C.c_void_p), i32, i32, C.c_size_t, vp]
+        lib.lgr_multimem_allreduce.restype = i32
+        lib.lgr_multimem_allreduce.argtypes = [vp, i32, i32, C.c_size_t, vp]
         lib.lgr_sh_grad_from_views.restype = i32
         lib.lgr_sh_grad_from_views.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]
         lib.lgr_mark_visible.restype = i32

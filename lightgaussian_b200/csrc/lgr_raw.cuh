@@ -468,6 +468,38 @@ __global__ void __launch_bounds__(512) peer_allreduce_kernel(PeerPtrs bufs, int 
     }
 }
 
+// The same all-reduce with the reduction done IN the NVSwitch (NVLS): `mc` is the multicast mapping of the symmetric buffer.
+// multimem.ld_reduce returns the sum over all ranks of the addressed 16 bytes (one response crosses this GPU's link instead
+// of world-1), multimem.st writes it to every rank.  Per GPU: n/world floats reduced in + n/world floats broadcast out, plus
+// serving the other ranks' reads -- ~1.5x (N=4) to ~1.75x (N=8) less NVLink traffic than the peer-pointer two-shot.
+__global__ void __launch_bounds__(512) multimem_allreduce_kernel(float* mc, int rank, int world, size_t n_vec4)
+{
+    const size_t per = (n_vec4 + world - 1) / world;
+    const size_t lo = per * rank, hi = min(n_vec4, lo + per);
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    constexpr int U = 4;
+    for (size_t base = lo + (size_t)blockIdx.x * blockDim.x + threadIdx.x; base < hi; base += stride * U) {
+        float4 acc[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const size_t i = base + u * stride;
+            if (i < hi)
+                asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                             : "=f"(acc[u].x), "=f"(acc[u].y), "=f"(acc[u].z), "=f"(acc[u].w)
+                             : "l"(reinterpret_cast<float4*>(mc) + i)
+                             : "memory");
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const size_t i = base + u * stride;
+            if (i < hi)
+                asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(reinterpret_cast<float4*>(mc) + i),
+                             "f"(acc[u].x), "f"(acc[u].y), "f"(acc[u].z), "f"(acc[u].w)
+                             : "memory");
+        }
+    }
+}
+
 // important_score for the raw path: the activated opacity lives in conic_opacity.w (rows of culled Gaussians are unwritten)
 __global__ void __launch_bounds__(256) score_from_geom_kernel(int P, const int* __restrict__ count, const float4* __restrict__ conic_opacity,
                                                               float* __restrict__ score)

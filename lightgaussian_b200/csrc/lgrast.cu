@@ -1378,6 +1378,22 @@ int lgr_peer_allreduce(float* const* peer_buffers, int rank, int world, size_t n
     return LGR_OK;
 }
 
+int lgr_multimem_allreduce(float* multicast_ptr, int rank, int world, size_t n_floats, void* cuda_stream)
+{
+    if (world < 1 || rank < 0 || rank >= world || !multicast_ptr || (n_floats & 3) || ((uintptr_t)multicast_ptr & 15)) {
+        g_last_error = "lgr_multimem_allreduce: bad argument";
+        return LGR_ERR_INVALID_ARG;
+    }
+    if (world == 1 || n_floats == 0) return LGR_OK;
+    cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+    {
+        ProfScope ps(ST_PEER_ALLREDUCE, stream);
+        multimem_allreduce_kernel<<<148 * 2, 512, 0, stream>>>(multicast_ptr, rank, world, n_floats / 4);
+    }
+    LGR_LAUNCH_CHECK("multimem_allreduce_kernel", false, stream);
+    return LGR_OK;
+}
+
 int lgr_sh_grad_from_views(int P, int M, int sh_degree, int n_views, const float* xyz, const float* campos, const float* d_rgb,
                            float* d_features_dc, float* d_features_rest, void* cuda_stream)
 {

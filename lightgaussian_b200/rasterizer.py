@@ -384,6 +384,9 @@ class _SymmExchange:
             ptrs = [int(p) for p in h.buffer_ptrs]
             assert len(ptrs) == world and all(ptrs)
             self.ptr_tables.append((C.c_void_p * world)(*ptrs))
+        self.mc_ptrs = [int(getattr(h, "multicast_ptr", 0) or 0) for h in self.hdls]
+        import os
+        self.mode = os.environ.get("LGR_EXCHANGE_REDUCE", "multimem" if all(self.mc_ptrs) else "peer")
         self.turn = 0
 
     def next(self):
@@ -395,7 +398,10 @@ class _SymmExchange:
         assert buf.data_ptr() == self.bufs[k].data_ptr()
         h = self.hdls[k]
         h.barrier(channel=0)      # every rank's K7+K8 has written its buffer
-        st = capi.load().lgr_peer_allreduce(self.ptr_tables[k], self.rank, self.world, self.n, stream.cuda_stream)
+        if self.mode == "multimem" and self.mc_ptrs[k]:
+            st = capi.load().lgr_multimem_allreduce(self.mc_ptrs[k], self.rank, self.world, self.n, stream.cuda_stream)
+        else:
+            st = capi.load().lgr_peer_allreduce(self.ptr_tables[k], self.rank, self.world, self.n, stream.cuda_stream)
         capi.check(st, "lgr_peer_allreduce")
         h.barrier(channel=1)      # every peer's stores into this rank's buffer have landed
 
