@@ -386,7 +386,9 @@ class _SymmExchange:
             self.ptr_tables.append((C.c_void_p * world)(*ptrs))
         self.mc_ptrs = [int(getattr(h, "multicast_ptr", 0) or 0) for h in self.hdls]
         import os
-        self.mode = os.environ.get("LGR_EXCHANGE_REDUCE", "multimem" if all(self.mc_ptrs) else "peer")
+        self.mode = os.environ.get("LGR_EXCHANGE_REDUCE", "peer")
+        if self.mode == "multimem" and not all(self.mc_ptrs):
+            self.mode = "peer"
         self.turn = 0
 
     def next(self):
@@ -416,7 +418,10 @@ def _symm_exchange(device, P, world, group):
     key = (str(device), P, world)
     if key not in _symm_cache:
         xb, ok = None, 1
-        if os.environ.get("LGR_PEER_ALLREDUCE", "1") == "0":
+        # Measured on 2 and 4 B200s: NCCL's all-reduce is as fast or faster than our peer-memory and
+        # NVLS multimem kernels for this 132 MB payload once the rebuild kernel competes for HBM, so NCCL is the default;
+        # LGR_EXCHANGE_REDUCE=peer|multimem selects ours.
+        if os.environ.get("LGR_EXCHANGE_REDUCE", "nccl") == "nccl":
             ok = 0
         else:
             try:
