@@ -654,7 +654,7 @@ __device__ __forceinline__ void red_flush(float* __restrict__ red, const uint32_
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 5)
 blend_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H, int tiles_x,
                       const float2* __restrict__ means2D, const float4* __restrict__ conic_opacity, const float4* __restrict__ rgb,
                       const float* __restrict__ bg, const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib,
