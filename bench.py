@@ -180,11 +180,14 @@ def cpu_oracle_sample(scene, cam, W, H):
 def main():
     args = parse_args()
     from lightgaussian_b200 import parallel
-    rank, world, local = parallel.init_from_env()
-    if args.impl == "reference" and rank != 0:
-        return 0  # the reference is single-GPU: rank 0 alone runs it
     if args.impl == "reference":
-        world = 1
+        # the reference is single-GPU (utils/general_utils.py:151 pins cuda:0): under torchrun rank 0 alone runs it, the other
+        # ranks exit without joining any process group
+        if int(os.environ.get("RANK", "0")) != 0:
+            return 0
+        rank, world, local = 0, 1, int(os.environ.get("LOCAL_RANK", "0"))
+    else:
+        rank, world, local = parallel.init_from_env()
     assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU path in the product)"
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
