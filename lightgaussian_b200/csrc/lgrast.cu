@@ -20,6 +20,7 @@
 //   preprocess_backward_kernel  conic/mean2D/colour gradients -> all dense per-Gaussian outputs  (K7+K8 fused)
 #include <cuda_runtime.h>
 #include <cub/cub.cuh>
+#include <thrust/iterator/transform_iterator.h>
 #include <atomic>
 #include <cstdio>
 #include <cstring>
@@ -171,7 +172,7 @@ GeometryState carve_geometry(char* base, size_t P)
     size_t sort_bytes = 0, scan_bytes = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr,
                                     (uint32_t*)nullptr, (int)P, 0, 32);
-    cub::TransformInputIterator<unsigned long long, TilesTouchedOp, const uint32_t*> it(nullptr, TilesTouchedOp{nullptr, nullptr});
+    auto it = thrust::make_transform_iterator((const uint32_t*)nullptr, TilesTouchedOp{nullptr, nullptr});
     cub::DeviceScan::InclusiveSum(nullptr, scan_bytes, it, (unsigned long long*)nullptr, (int)P);
     g.cub_temp_bytes = sort_bytes > scan_bytes ? sort_bytes : scan_bytes;
     g.cub_temp = c.take<char>(g.cub_temp_bytes);
@@ -1032,7 +1033,7 @@ int forward_impl(const lgr_view* v, int P, int M, const float* means3D, const fl
             LGR_CUDA_TRY(cub::DeviceRadixSort::SortPairs(geo.cub_temp, tmp, (const uint32_t*)geo.depth_keys, geo.depth_keys_sorted,
                                                           (const uint32_t*)geo.iota, geo.sorted_ids, P, 0, 32, stream));
         }
-        cub::TransformInputIterator<unsigned long long, TilesTouchedOp, const uint32_t*> it(geo.sorted_ids, TilesTouchedOp{geo.tiles_kept, geo.tiles_touched});
+            auto it = thrust::make_transform_iterator((const uint32_t*)geo.sorted_ids, TilesTouchedOp{geo.tiles_kept, geo.tiles_touched});
         tmp = geo.cub_temp_bytes;
         {
             ProfScope ps(ST_SCAN, stream);
