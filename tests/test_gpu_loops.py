@@ -1,0 +1,131 @@
+"""The loops the reference drives through render()/count_render() -- significance pruning (prune.py:112-157 +
+gaussian_model.py:776-782), prune-finetune iterations (prune_finetune.py:144-166, 287-289) and an SH-distillation step
+(distill_train.py:124-166) -- restated on small synthetic scenes on top of OUR packages, including a side-by-side run of the
+same optimisation with the reference's own kernels."""
+import copy
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from lightgaussian_b200.model import GaussianParams, TorchCamera, pipeline_params
+from lightgaussian_b200.renderer import render, count_render
+from lightgaussian_b200.synth import make_scene, make_cameras
+from lightgaussian_b200 import parallel
+
+pytestmark = pytest.mark.gpu
+
+W, H = 192, 144
+
+
+def psnr(a, b):
+    mse = float(((a - b) ** 2).mean())
+    return 99.0 if mse == 0 else 10.0 * math.log10(1.0 / mse)
+
+
+def _scene(P=6000, seed=41, requires_grad=True):
+    scene = make_scene(P, sh_degree=3, seed=seed, scale_mult=1.6)
+    pc = GaussianParams(scene["raw"], 3, "cuda", requires_grad=requires_grad)
+    cams = [TorchCamera(c, "cuda") for c in make_cameras(8, W, H)]
+    return scene, pc, cams, pipeline_params(), torch.zeros(3, device="cuda")
+
+
+def _v_imp_score(pc, imp, v_pow=0.1):
+    """prune.calculate_v_imp_score (prune.py:112-128)"""
+    volume = torch.prod(pc.get_scaling, dim=1)
+    kth = torch.sort(volume, descending=True)[0][int(len(volume) * 0.9)]
+    return torch.pow(volume / kth, v_pow) * imp
+
+
+def _prune_mask(score, percent):
+    """GaussianModel.prune_gaussians (gaussian_model.py:776-782): ties at the threshold are pruned"""
+    thr = torch.sort(score)[0][int(percent * (score.shape[0] - 1))]
+    return score <= thr
+
+
+def _keep(pc, keep):
+    sub = copy.copy(pc)
+    for n in ("_xyz", "_features_dc", "_features_rest", "_scaling", "_rotation", "_opacity"):
+        setattr(sub, n, getattr(pc, n).detach()[keep].contiguous())
+    return sub
+
+
+def test_significance_pruning_keeps_the_image():
+    _, pc, cams, pipe, bg = _scene(requires_grad=False)
+    with torch.no_grad():
+        cnt, imp = parallel.sharded_prune_list(pc, cams, pipe, bg, count_render, 0, 1)
+        # prune.prune_list semantics: plain sums of the per-view outputs
+        manual = sum(count_render(c, pc, pipe, bg)["gaussians_count"].to(torch.int64) for c in cams)
+        assert torch.equal(cnt, manual)
+        score = _v_imp_score(pc, imp)
+        mask = _prune_mask(score, 0.4)
+        assert abs(int(mask.sum()) - 0.4 * score.shape[0]) <= 0.02 * score.shape[0] + (score == 0).sum().item()
+        full = [render(c, pc, pipe, bg)["render"] for c in cams]
+        by_score = _keep(pc, ~mask)
+        g = torch.Generator().manual_seed(0)
+        rnd = torch.rand(score.shape[0], generator=g).cuda() < mask.float().mean()
+        by_chance = _keep(pc, ~rnd)
+        p_score = np.mean([psnr(render(c, by_score, pipe, bg)["render"], f) for c, f in zip(cams, full)])
+        p_rand = np.mean([psnr(render(c, by_chance, pipe, bg)["render"], f) for c, f in zip(cams, full)])
+    assert p_score > p_rand + 3.0, (p_score, p_rand)      # the significance score finds the Gaussians that do not matter
+
+
+def _finetune(render_fn, raw, cams, targets, steps=60):
+    pc = GaussianParams(raw, 3, "cuda")
+    # per-group learning rates in the spirit of GaussianModel.training_setup (scene/gaussian_model.py:184-217)
+    opt = torch.optim.Adam([{"params": [pc._xyz], "lr": 1e-4}, {"params": [pc._features_dc], "lr": 1e-2},
+                            {"params": [pc._features_rest], "lr": 5e-4}, {"params": [pc._opacity], "lr": 5e-2},
+                            {"params": [pc._scaling], "lr": 5e-3}, {"params": [pc._rotation], "lr": 1e-3}], lr=0.0, eps=1e-15)
+    pipe, bg = pipeline_params(), torch.zeros(3, device="cuda")
+    losses = []
+    for it in range(steps):
+        i = it % len(cams)
+        loss = (render_fn(cams[i], pc, pipe, bg)["render"] - targets[i]).abs().mean()   # l1_loss, utils/loss_utils.py:18
+        loss.backward()
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        losses.append(float(loss))
+    return losses, pc
+
+
+def test_finetune_converges_like_the_reference_kernels():
+    scene, pc, cams, pipe, bg = _scene(P=5000, seed=43, requires_grad=False)
+    with torch.no_grad():
+        targets = [render(c, pc, pipe, bg)["render"].clone() for c in cams]
+    rng = np.random.default_rng(0)
+    raw = {k: v.copy() for k, v in scene["raw"].items()}
+    raw["features_dc"] += 0.5 * rng.standard_normal(raw["features_dc"].shape).astype(np.float32)
+    raw["opacity"] += 1.0 * rng.standard_normal(raw["opacity"].shape).astype(np.float32)
+    raw["xyz"] += 0.004 * rng.standard_normal(raw["xyz"].shape).astype(np.float32)
+    ours, _ = _finetune(render, raw, cams, targets)
+    assert np.mean(ours[-8:]) < 0.85 * np.mean(ours[:8]), ours
+    import bench
+    ref_render = bench.make_reference_render()
+    if ref_render is None:
+        pytest.skip("oracle/_ref/libref_rasterizer.so not built")
+    ref, _ = _finetune(lambda cam, pc_, pipe_, bg_: ref_render(cam, pc_, pipe_, bg_), raw, cams, targets)
+    assert abs(ours[0] - ref[0]) < 1e-6                                  # same forward
+    assert abs(np.mean(ours[-8:]) - np.mean(ref[-8:])) < 0.03 * np.mean(ref[-8:]), (ours[-8:], ref[-8:])
+
+
+def test_distillation_step_student_sh2_from_teacher_sh3():
+    scene, teacher, cams, pipe, bg = _scene(P=4000, seed=47, requires_grad=False)
+    raw = {k: v.copy() for k, v in scene["raw"].items()}
+    raw["features_rest"] = np.ascontiguousarray(raw["features_rest"][:, :8])        # onedownSHdegree: keep (2+1)^2-1 coefficients
+    student = GaussianParams(raw, 3, "cuda")
+    student.max_sh_degree = student.active_sh_degree = 2
+    opt = torch.optim.Adam([student._features_dc, student._features_rest], lr=0.01, eps=1e-15)
+    losses = []
+    for it in range(30):
+        cam = cams[it % len(cams)]
+        with torch.no_grad():
+            t_img = render(cam, teacher, pipe, bg)["render"]
+        s_img = render(cam, student, pipe, bg)["render"]
+        loss = (s_img - t_img).abs().mean()
+        loss.backward()
+        assert student._features_rest.grad.shape == (4000, 8, 3) and torch.isfinite(student._features_rest.grad).all()
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        losses.append(float(loss))
+    assert losses[0] > 0 and np.mean(losses[-5:]) < 0.9 * np.mean(losses[:5]), losses
