@@ -403,6 +403,38 @@ def main():
         signif = {"value": nsig * world / (t_sig * 1e-3), "unit": "views/s", "views": nsig * world,
                   "what": "count_render() (forward + exact Global Significance counts), cameras sharded over ranks"}
 
+    # ---------------- image-loss pass (row N2): (1-l)*L1 + l*(1-SSIM) forward+backward on one HxW image ----------------
+    loss_pass = None
+    if args.impl == "ours" and not args.no_roofline and world == 1:
+        from lightgaussian_b200 import loss as fused_loss
+        import torch.nn.functional as F
+        gimg = torch.rand(3, H, W, device=dev)
+        gtgt = torch.rand(3, H, W, device=dev)
+        g1 = torch.tensor([math.exp(-((k - 5) ** 2) / (2 * 1.5 ** 2)) for k in range(11)], device=dev)
+        g1 = g1 / g1.sum()
+        w2 = (g1[:, None] * g1[None, :]).expand(3, 1, 11, 11).contiguous()
+
+        def torch_loss(x, y):                      # op-for-op what utils/loss_utils.py launches (5 conv2d + elementwise + autograd)
+            cv = lambda t: F.conv2d(t[None], w2, padding=5, groups=3)[0]  # noqa: E731
+            mu1, mu2 = cv(x), cv(y)
+            s1, s2, s12 = cv(x * x) - mu1 * mu1, cv(y * y) - mu2 * mu2, cv(x * y) - mu1 * mu2
+            m = ((2 * mu1 * mu2 + 1e-4) * (2 * s12 + 9e-4)) / ((mu1 * mu1 + mu2 * mu2 + 1e-4) * (s1 + s2 + 9e-4))
+            return 0.8 * (x - y).abs().mean() + 0.2 * (1.0 - m.mean())
+
+        def run(fn):
+            def step(_s):
+                x = gimg.detach().requires_grad_(True)
+                fn(x, gtgt).backward()
+            for _ in range(3):
+                step(0)
+            t, _ = timed(step, 20)
+            return t / 20
+        t_f = run(lambda x, y: fused_loss.l1_ssim_loss(x, y, 0.2))
+        t_t = run(torch_loss)
+        loss_pass = {"fused_ms": t_f, "torch_composed_ms": t_t, "image": [3, H, W],
+                     "alg_bytes": 3 * H * W * 4 * (2 + 3 + 2 + 3 + 1),
+                     "what": "l1_ssim_loss forward+backward (lgr_image_loss_forward/backward) vs the reference's torch op sequence"}
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         if args.impl == "ours":
@@ -444,6 +476,8 @@ def main():
             line["stages"] = stages
         if signif:
             line["significance_pass"] = signif
+        if loss_pass:
+            line["loss_pass"] = loss_pass
         if cpu_baseline:
             line["cpu_baseline"] = cpu_baseline
         print(json.dumps(line))

@@ -162,6 +162,18 @@ int lgr_peer_allreduce(float* const* peer_buffers, int rank, int world, size_t n
  * of the symmetric buffer (multimem.ld_reduce / multimem.st).  Barriers before and after are the caller's. */
 int lgr_multimem_allreduce(float* multicast_ptr, int rank, int world, size_t n_floats, void* cuda_stream);
 
+/* ---- fused image loss of the training loops (utils/loss_utils.py:18-85) ----
+ * forward: out2[0] = mean|img - target| (l1_loss), out2[1] = ssim(img, target) (11x11 Gaussian window, sigma 1.5, zero padding,
+ * C1 = 0.01^2, C2 = 0.03^2, mean over C*H*W).  dmaps (optional, [3,C,H,W]) receives what the backward needs.  All device
+ * pointers; planar [C,H,W] float32.  workspace: lgr_image_loss_workspace_bytes() bytes, 8-byte aligned.
+ * backward: d_img = s * d/d img ( g_l1 * l1 + g_ssim * ssim ),  s = *grad_scale (device scalar) or 1 when NULL.
+ * The reference's training loss (1-l)*l1 + l*(1-ssim) (prune_finetune.py:160-164) is g_l1 = 1-l, g_ssim = -l. */
+size_t lgr_image_loss_workspace_bytes(int C, int H, int W);
+int lgr_image_loss_forward(const float* img, const float* target, int C, int H, int W, float* out2, float* dmaps, void* workspace,
+                           void* cuda_stream);
+int lgr_image_loss_backward(const float* img, const float* target, const float* dmaps, int C, int H, int W, float g_l1, float g_ssim,
+                            const float* grad_scale, float* d_img, void* cuda_stream);
+
 /* present[i] = (view-space z of point i) > 0.2   (RAST/cuda_rasterizer/rasterizer_impl.cu:54-66, auxiliary.h:139-164) */
 int lgr_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix, uint8_t* present,
                      void* cuda_stream);

@@ -82,6 +82,12 @@ def load():
         lib.lgr_backward_raw_end.argtypes = [C.POINTER(LgrView), i32, i32, C.POINTER(LgrRawParams), vp, vp, C.POINTER(LgrRawGrads), vp, vp]
         lib.lgr_peer_allreduce.restype = i32
         lib.lgr_peer_allreduce.argtypes = [C.POINTER(C.c_void_p), i32, i32, C.c_size_t, vp]
+        lib.lgr_image_loss_workspace_bytes.restype = C.c_size_t
+        lib.lgr_image_loss_workspace_bytes.argtypes = [i32, i32, i32]
+        lib.lgr_image_loss_forward.restype = i32
+        lib.lgr_image_loss_forward.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp]
+        lib.lgr_image_loss_backward.restype = i32
+        lib.lgr_image_loss_backward.argtypes = [vp, vp, vp, i32, i32, i32, C.c_float, C.c_float, vp, vp, vp]
         lib.lgr_multimem_allreduce.restype = i32
         lib.lgr_multimem_allreduce.argtypes = [vp, i32, i32, C.c_size_t, vp]
         lib.lgr_sh_grad_from_views.restype = i32

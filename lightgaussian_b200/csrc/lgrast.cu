@@ -44,11 +44,11 @@ std::atomic<uint64_t> g_launches{0};
 
 // ---- optional per-stage device timing (CUDA events on the launch stream), used by bench.py's roofline ----
 enum StageId { ST_PREPROCESS = 0, ST_DEPTH_SORT, ST_SCAN, ST_EMIT, ST_TILE_SORT, ST_RANGES, ST_BLEND_FWD, ST_BLEND_FWD_COUNT,
-               ST_SCORE, ST_BLEND_BWD, ST_PREPROCESS_BWD, ST_MEMSET, ST_SH_GRAD, ST_PEER_ALLREDUCE, ST_COUNT };
+               ST_SCORE, ST_BLEND_BWD, ST_PREPROCESS_BWD, ST_MEMSET, ST_SH_GRAD, ST_PEER_ALLREDUCE, ST_LOSS_FWD, ST_LOSS_BWD, ST_COUNT };
 const char* const kStageNames[ST_COUNT] = {"preprocess_kernel", "depth_sort(cub)", "scan(cub)", "emit_kernel", "tile_sort(cub)",
                                            "ranges_kernel", "blend_forward_kernel", "blend_forward_kernel<count>", "score_kernel",
                                            "blend_backward_kernel", "preprocess_backward_kernel", "memset", "sh_grad_from_views_kernel",
-                                           "peer_allreduce_kernel"};
+                                           "peer_allreduce_kernel", "image_loss_forward_kernel", "image_loss_backward_kernel"};
 struct ProfRecord { int stage; cudaEvent_t a, b; };
 bool g_prof_on = false;
 std::vector<ProfRecord> g_prof_records;
@@ -913,6 +913,7 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(PreBackArgs a)
 
 }  // namespace
 #include "lgr_raw.cuh"
+#include "lgr_loss.cuh"
 namespace {
 
 // ------------------------------------------------------------------------------------------------
@@ -1413,6 +1414,64 @@ int lgr_sh_grad_from_views(int P, int M, int sh_degree, int n_views, const float
         sh_grad_from_views_kernel<<<(P + 255) / 256, 256, smem, stream>>>(a);
     }
     LGR_LAUNCH_CHECK("sh_grad_from_views_kernel", false, stream);
+    return LGR_OK;
+}
+
+// ---- fused image loss (row N2): utils/loss_utils.py l1_loss + ssim and their backward ----
+static LossWindow make_loss_window()
+{
+    // gaussian(11, 1.5) of utils/loss_utils.py:26-33: float32 taps, normalised by their float32 sum
+    LossWindow w;
+    float sum = 0.f;
+    for (int k = 0; k < 11; k++) {
+        w.g[k] = (float)exp(-(double)((k - 5) * (k - 5)) / (2.0 * 1.5 * 1.5));
+        sum += w.g[k];
+    }
+    for (int k = 0; k < 11; k++) w.g[k] = w.g[k] / sum;
+    return w;
+}
+
+size_t lgr_image_loss_workspace_bytes(int C, int H, int W)
+{
+    const size_t blocks = (size_t)((W + LT - 1) / LT) * ((H + LT - 1) / LT) * (size_t)(C > 0 ? C : 0);
+    return blocks * sizeof(float2) + 256;
+}
+
+int lgr_image_loss_forward(const float* img, const float* target, int C, int H, int W, float* out2, float* dmaps, void* workspace,
+                           void* cuda_stream)
+{
+    if (!img || !target || !out2 || !workspace || C <= 0 || H <= 0 || W <= 0 || ((uintptr_t)workspace & 7)) {
+        g_last_error = "lgr_image_loss_forward: bad argument";
+        return LGR_ERR_INVALID_ARG;
+    }
+    cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+    const dim3 grid((W + LT - 1) / LT, (H + LT - 1) / LT, C);
+    const int nblocks = (int)(grid.x * grid.y * grid.z);
+    {
+        ProfScope ps(ST_LOSS_FWD, stream);
+        image_loss_forward_kernel<<<grid, 256, 0, stream>>>(img, target, C, H, W, make_loss_window(), dmaps, (float2*)workspace);
+        image_loss_finish_kernel<<<1, 256, 0, stream>>>((const float2*)workspace, nblocks, 1.0 / ((double)C * H * W), out2);
+    }
+    LGR_LAUNCH_CHECK("image_loss_forward_kernel", false, stream);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return LGR_OK;
+}
+
+int lgr_image_loss_backward(const float* img, const float* target, const float* dmaps, int C, int H, int W, float g_l1, float g_ssim,
+                            const float* grad_scale, float* d_img, void* cuda_stream)
+{
+    if (!img || !target || !d_img || C <= 0 || H <= 0 || W <= 0 || (g_ssim != 0.f && !dmaps)) {
+        g_last_error = "lgr_image_loss_backward: bad argument";
+        return LGR_ERR_INVALID_ARG;
+    }
+    cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+    const dim3 grid((W + LT - 1) / LT, (H + LT - 1) / LT, C);
+    {
+        ProfScope ps(ST_LOSS_BWD, stream);
+        image_loss_backward_kernel<<<grid, 256, 0, stream>>>(img, target, dmaps, C, H, W, make_loss_window(), g_l1, g_ssim, grad_scale,
+                                                              (float)(1.0 / ((double)C * H * W)), d_img);
+    }
+    LGR_LAUNCH_CHECK("image_loss_backward_kernel", false, stream);
     return LGR_OK;
 }
 

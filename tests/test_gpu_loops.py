@@ -85,7 +85,7 @@ def _finetune(render_fn, raw, cams, targets, steps=60):
         loss.backward()
         opt.step()
         opt.zero_grad(set_to_none=True)
-        losses.append(float(loss))
+        losses.append(float(loss.detach()))
     return losses, pc
 
 
@@ -127,5 +127,5 @@ def test_distillation_step_student_sh2_from_teacher_sh3():
         assert student._features_rest.grad.shape == (4000, 8, 3) and torch.isfinite(student._features_rest.grad).all()
         opt.step()
         opt.zero_grad(set_to_none=True)
-        losses.append(float(loss))
+        losses.append(float(loss.detach()))
     assert losses[0] > 0 and np.mean(losses[-5:]) < 0.9 * np.mean(losses[:5]), losses

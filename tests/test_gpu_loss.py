@@ -1,0 +1,124 @@
+"""GPU parity of the fused image loss (row N2): lgr_image_loss_forward/backward through lightgaussian_b200.loss and the
+`utils.loss_utils` drop-in, against the float64 oracle (oracle/loss_oracle.py), the reference-module golden
+(tests/golden/pyref_loss.npz) and a torch restatement at 1080p.
+Tolerances: values 1e-5 abs (the SSIM moments cancel in fp32: the reference's own fp32 CPU result is 2e-6 from float64),
+gradients 1e-3 of the gradient's max (north_star: gradients 1e-3 rel)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from lightgaussian_b200 import loss as fused
+from oracle import loss_oracle as lo
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pyref_loss.npz")
+
+
+def _pair(C, H, W, seed):
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:H, 0:W]
+    base = 0.5 + 0.4 * np.sin(xx / 9.0)[None] * np.cos(yy / 6.0)[None] * np.linspace(1.0, 0.4, C)[:, None, None]
+    x = np.clip(base + 0.1 * rng.standard_normal((C, H, W)), 0, 1.4).astype(np.float32)
+    y = np.clip(base + 0.05 * rng.standard_normal((C, H, W)), 0, 1).astype(np.float32)
+    return x, y
+
+
+@pytest.mark.parametrize("name", ["a", "b", "c"])
+def test_against_reference_module_golden(name):
+    g = np.load(GOLD)
+    x = torch.from_numpy(g[f"{name}_x"]).cuda().requires_grad_(True)
+    y = torch.from_numpy(g[f"{name}_y"]).cuda()
+    l1, ss = fused.l1_loss(x, y), fused.ssim(x, y)
+    assert abs(float(l1.detach()) - float(g[f"{name}_l1"])) < 1e-6
+    assert abs(float(ss.detach()) - float(g[f"{name}_ssim"])) < 1e-5
+    loss = 0.8 * l1 + 0.2 * (1.0 - ss)                       # the reference's two-call form
+    loss.backward()
+    ref = g[f"{name}_grad"]
+    assert np.abs(x.grad.cpu().numpy() - ref).max() <= 1e-3 * np.abs(ref).max()
+    x2 = x.detach().clone().requires_grad_(True)
+    one = fused.l1_ssim_loss(x2, y, 0.2)                      # the single-kernel form
+    assert abs(float(one.detach()) - float(g[f"{name}_loss"])) < 1e-5
+    one.backward()
+    assert np.abs(x2.grad.cpu().numpy() - ref).max() <= 1e-3 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("shape", [(3, 1, 1), (3, 5, 70), (1, 33, 31), (3, 96, 128), (4, 65, 97)])
+def test_against_oracle_ragged_sizes(shape):
+    xn, yn = _pair(*shape, seed=sum(shape))
+    x, y = torch.from_numpy(xn).cuda().requires_grad_(True), torch.from_numpy(yn).cuda()
+    l1, ss, _ = lo.l1_ssim(xn, yn)
+    out = fused.l1_ssim_loss(x, y, 0.2)
+    assert abs(float(out.detach()) - (0.8 * l1 + 0.2 * (1 - ss))) < 1e-5
+    (3.0 * out).backward()                                    # upstream scale goes through the device scalar
+    ref = 3.0 * lo.grad_wrt_first(xn, yn, 0.8, -0.2)
+    assert np.abs(x.grad.cpu().numpy() - ref).max() <= 1e-3 * np.abs(ref).max()
+
+
+def test_identical_images_and_determinism():
+    xn, _ = _pair(3, 50, 60, 5)
+    x = torch.from_numpy(xn).cuda()
+    assert float(fused.l1_loss(x, x)) == 0.0
+    assert abs(float(fused.ssim(x, x)) - 1.0) < 1e-6
+    xr = x.clone().requires_grad_(True)
+    fused.l1_loss(xr, x).backward()
+    assert float(xr.grad.abs().max()) == 0.0                  # torch.sign(0) = 0
+    y = torch.from_numpy(_pair(3, 50, 60, 6)[1]).cuda()
+    a, b = fused.l1_ssim_loss(x, y), fused.l1_ssim_loss(x, y)
+    assert float(a) == float(b)                               # fixed reduction order
+
+
+def _torch_ssim(img1, img2):
+    """torch restatement of utils/loss_utils.py:45-85 for the full-size check"""
+    g = torch.from_numpy(lo.window_2d()).to(img1.device)
+    C = img1.shape[0]
+    w = g.expand(C, 1, 11, 11).contiguous()
+    conv = lambda t: F.conv2d(t[None], w, padding=5, groups=C)[0]  # noqa: E731
+    mu1, mu2 = conv(img1), conv(img2)
+    s1, s2, s12 = conv(img1 * img1) - mu1 * mu1, conv(img2 * img2) - mu2 * mu2, conv(img1 * img2) - mu1 * mu2
+    C1, C2 = 0.01 ** 2, 0.03 ** 2
+    return (((2 * mu1 * mu2 + C1) * (2 * s12 + C2)) / ((mu1 * mu1 + mu2 * mu2 + C1) * (s1 + s2 + C2))).mean()
+
+
+def test_full_size_1080p_against_torch_double():
+    xn, yn = _pair(3, 1080, 1920, 11)
+    x, y = torch.from_numpy(xn).cuda().requires_grad_(True), torch.from_numpy(yn).cuda()
+    out = fused.l1_ssim_loss(x, y, 0.2)
+    out.backward()
+    xd, yd = x.detach().double().requires_grad_(True), y.double()
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        ref = 0.8 * (xd - yd).abs().mean() + 0.2 * (1.0 - _torch_ssim(xd, yd))
+        ref.backward()
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    assert abs(float(out.detach()) - float(ref.detach())) < 1e-5
+    assert float((x.grad.double() - xd.grad).abs().max()) <= 1e-3 * float(xd.grad.abs().max())
+
+
+def test_dropin_loss_utils_accepts_metrics_py_batches():
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "dropin"))
+    try:
+        for m in [k for k in sys.modules if k == "utils" or k.startswith("utils.")]:
+            del sys.modules[m]
+        from utils.loss_utils import l1_loss, ssim, l2_loss
+        xn, yn = _pair(3, 40, 48, 21)
+        x, y = torch.from_numpy(xn).cuda(), torch.from_numpy(yn).cuda()
+        l1, ss, _ = lo.l1_ssim(xn, yn)
+        assert abs(float(ssim(x[None], y[None])) - ss) < 1e-5          # metrics.py:71 passes [1,3,H,W]
+        assert abs(float(l1_loss(x, y)) - l1) < 1e-6
+        assert abs(float(l2_loss(x, y)) - float(((xn - yn) ** 2).mean())) < 1e-6
+    finally:
+        sys.path.pop(0)
+        for m in [k for k in sys.modules if k == "utils" or k.startswith("utils.")]:
+            del sys.modules[m]
+
+
+def test_cpu_tensors_are_refused():
+    with pytest.raises(RuntimeError):
+        fused.l1_loss(torch.zeros(3, 4, 4), torch.zeros(3, 4, 4))
