@@ -174,6 +174,37 @@ int lgr_image_loss_forward(const float* img, const float* target, int C, int H, 
 int lgr_image_loss_backward(const float* img, const float* target, const float* dmaps, int C, int H, int W, float g_l1, float g_ssim,
                             const float* grad_scale, float* d_img, void* cuda_stream);
 
+/* ---- optimizer side of the training loops ----
+ * lgr_adamw_step: torch.optim.AdamW's default (foreach) update, amsgrad off, for up to 8 tensors in ONE launch; replaces
+ * `gaussians.optimizer.step()` (prune_finetune.py:287, optimizer built at scene/gaussian_model.py:184-217).  `step` is the
+ * tensor's step count AFTER the increment (t >= 1); lr is per tensor (one per param group), the rest is shared.  The host
+ * scalars are formed in double precision exactly as torch/optim/adam.py does and rounded to fp32 at the kernel boundary. */
+typedef struct lgr_adamw_tensor {
+    float* param;
+    const float* grad;
+    float* exp_avg;
+    float* exp_avg_sq;
+    int64_t numel;
+    double lr;
+    double step;
+} lgr_adamw_tensor;
+int lgr_adamw_step(int n_tensors, const lgr_adamw_tensor* tensors, double beta1, double beta2, double eps, double weight_decay,
+                   void* cuda_stream);
+
+/* Row compaction of GaussianModel._prune_optimizer / prune_points (scene/gaussian_model.py:564-600): `keep` is a device byte
+ * mask over P rows.  lgr_compact_plan writes the indices of the kept rows, ascending, to src_row[0..rows_out) and returns
+ * rows_out through a host pointer (one stream synchronisation); lgr_compact_rows then gathers up to 24 row-major tensors
+ * (row_words 4-byte words per row: parameters and both Adam moments of all groups) in ONE launch. */
+typedef struct lgr_compact_tensor {
+    const void* src;
+    void* dst;
+    int32_t row_words;
+} lgr_compact_tensor;
+size_t lgr_compact_workspace_bytes(int P);
+int lgr_compact_plan(int P, const uint8_t* keep, int32_t* src_row, void* workspace, size_t workspace_bytes, int32_t* rows_out_host,
+                     void* cuda_stream);
+int lgr_compact_rows(int rows_out, const int32_t* src_row, int n_tensors, const lgr_compact_tensor* tensors, void* cuda_stream);
+
 /* present[i] = (view-space z of point i) > 0.2   (RAST/cuda_rasterizer/rasterizer_impl.cu:54-66, auxiliary.h:139-164) */
 int lgr_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix, uint8_t* present,
                      void* cuda_stream);

@@ -38,6 +38,17 @@ class LgrRawGrads(C.Structure):
     _fields_ = LgrRawParams._fields_ + [("rgb", C.c_void_p)]
 
 
+class LgrAdamwTensor(C.Structure):
+    """struct lgr_adamw_tensor"""
+    _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
+                ("numel", C.c_int64), ("lr", C.c_double), ("step", C.c_double)]
+
+
+class LgrCompactTensor(C.Structure):
+    """struct lgr_compact_tensor"""
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("row_words", C.c_int32)]
+
+
 ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t)
 
 _lib = None
@@ -88,6 +99,14 @@ def load():
         lib.lgr_image_loss_forward.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp]
         lib.lgr_image_loss_backward.restype = i32
         lib.lgr_image_loss_backward.argtypes = [vp, vp, vp, i32, i32, i32, C.c_float, C.c_float, vp, vp, vp]
+        lib.lgr_adamw_step.restype = i32
+        lib.lgr_adamw_step.argtypes = [i32, C.POINTER(LgrAdamwTensor), C.c_double, C.c_double, C.c_double, C.c_double, vp]
+        lib.lgr_compact_workspace_bytes.restype = C.c_size_t
+        lib.lgr_compact_workspace_bytes.argtypes = [i32]
+        lib.lgr_compact_plan.restype = i32
+        lib.lgr_compact_plan.argtypes = [i32, vp, vp, vp, C.c_size_t, C.POINTER(C.c_int32), vp]
+        lib.lgr_compact_rows.restype = i32
+        lib.lgr_compact_rows.argtypes = [i32, vp, i32, C.POINTER(LgrCompactTensor), vp]
         lib.lgr_multimem_allreduce.restype = i32
         lib.lgr_multimem_allreduce.argtypes = [vp, i32, i32, C.c_size_t, vp]
         lib.lgr_sh_grad_from_views.restype = i32

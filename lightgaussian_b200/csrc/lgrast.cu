@@ -21,6 +21,8 @@
 #include <cuda_runtime.h>
 #include <cub/cub.cuh>
 #include <thrust/iterator/transform_iterator.h>
+#include <thrust/iterator/counting_iterator.h>
+#include <cmath>
 #include <atomic>
 #include <cstdio>
 #include <cstring>
@@ -44,11 +46,12 @@ std::atomic<uint64_t> g_launches{0};
 
 // ---- optional per-stage device timing (CUDA events on the launch stream), used by bench.py's roofline ----
 enum StageId { ST_PREPROCESS = 0, ST_DEPTH_SORT, ST_SCAN, ST_EMIT, ST_TILE_SORT, ST_RANGES, ST_BLEND_FWD, ST_BLEND_FWD_COUNT,
-               ST_SCORE, ST_BLEND_BWD, ST_PREPROCESS_BWD, ST_MEMSET, ST_SH_GRAD, ST_PEER_ALLREDUCE, ST_LOSS_FWD, ST_LOSS_BWD, ST_COUNT };
+               ST_SCORE, ST_BLEND_BWD, ST_PREPROCESS_BWD, ST_MEMSET, ST_SH_GRAD, ST_PEER_ALLREDUCE, ST_LOSS_FWD, ST_LOSS_BWD, ST_ADAMW, ST_COMPACT, ST_COUNT };
 const char* const kStageNames[ST_COUNT] = {"preprocess_kernel", "depth_sort(cub)", "scan(cub)", "emit_kernel", "tile_sort(cub)",
                                            "ranges_kernel", "blend_forward_kernel", "blend_forward_kernel<count>", "score_kernel",
                                            "blend_backward_kernel", "preprocess_backward_kernel", "memset", "sh_grad_from_views_kernel",
-                                           "peer_allreduce_kernel", "image_loss_forward_kernel", "image_loss_backward_kernel"};
+                                           "peer_allreduce_kernel", "image_loss_forward_kernel", "image_loss_backward_kernel", "adamw_multi_kernel",
+                                           "compact_gather_kernel"};
 struct ProfRecord { int stage; cudaEvent_t a, b; };
 bool g_prof_on = false;
 std::vector<ProfRecord> g_prof_records;
@@ -914,6 +917,7 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(PreBackArgs a)
 }  // namespace
 #include "lgr_raw.cuh"
 #include "lgr_loss.cuh"
+#include "lgr_optim.cuh"
 namespace {
 
 // ------------------------------------------------------------------------------------------------
@@ -1472,6 +1476,130 @@ int lgr_image_loss_backward(const float* img, const float* target, const float* 
                                                               (float)(1.0 / ((double)C * H * W)), d_img);
     }
     LGR_LAUNCH_CHECK("image_loss_backward_kernel", false, stream);
+    return LGR_OK;
+}
+
+// ---- optimizer (row N3) ----
+int lgr_adamw_step(int n_tensors, const lgr_adamw_tensor* tensors, double beta1, double beta2, double eps, double weight_decay,
+                   void* cuda_stream)
+{
+    if (n_tensors < 0 || n_tensors > OPT_MAX_TENSORS || (n_tensors && !tensors)) {
+        g_last_error = "lgr_adamw_step: between 0 and 8 tensors per call";
+        return LGR_ERR_INVALID_ARG;
+    }
+    AdamTable t;
+    memset(&t, 0, sizeof(t));
+    int k = 0;
+    long long chunks = 0;
+    for (int i = 0; i < n_tensors; i++) {
+        const lgr_adamw_tensor& a = tensors[i];
+        if (a.numel == 0) continue;
+        if (a.numel < 0 || !a.param || !a.grad || !a.exp_avg || !a.exp_avg_sq || a.step < 1.0) {
+            g_last_error = "lgr_adamw_step: tensor with a missing pointer, negative size or step < 1";
+            return LGR_ERR_INVALID_ARG;
+        }
+        // torch/optim/adam.py _multi_tensor_adam: python floats (double), then cast to the kernels' opmath type (float)
+        const double bc1 = 1.0 - pow(beta1, a.step), bc2 = 1.0 - pow(beta2, a.step);
+        t.p[k] = a.param; t.g[k] = a.grad; t.m[k] = a.exp_avg; t.v[k] = a.exp_avg_sq;
+        t.n[k] = a.numel;
+        t.decay[k] = (float)(1.0 - a.lr * weight_decay);
+        t.neg_step[k] = (float)((a.lr / bc1) * -1.0);
+        t.bc2_sqrt[k] = (float)pow(bc2, 0.5);
+        t.chunk_start[k] = (int)chunks;
+        chunks += (a.numel + OPT_CHUNK - 1) / OPT_CHUNK;
+        k++;
+    }
+    if (chunks > 0x7fffffffLL) {
+        g_last_error = "lgr_adamw_step: too many elements for one launch";
+        return LGR_ERR_INVALID_ARG;
+    }
+    for (int i = k; i <= OPT_MAX_TENSORS; i++) t.chunk_start[i] = (int)chunks;
+    t.count = k;
+    t.w1 = (float)(1.0 - beta1); t.beta2 = (float)beta2; t.w2 = (float)(1.0 - beta2); t.eps = (float)eps;
+    if (chunks == 0) return LGR_OK;
+    cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+    {
+        ProfScope ps(ST_ADAMW, stream);
+        adamw_multi_kernel<<<(unsigned)chunks, 256, 0, stream>>>(t);
+    }
+    LGR_LAUNCH_CHECK("adamw_multi_kernel", false, stream);
+    return LGR_OK;
+}
+
+static size_t compact_cub_bytes(int P)
+{
+    size_t bytes = 0;
+    cub::DeviceSelect::Flagged((void*)nullptr, bytes, thrust::counting_iterator<int>(0), (const uint8_t*)nullptr, (int*)nullptr, (int*)nullptr, P);
+    return bytes;
+}
+
+size_t lgr_compact_workspace_bytes(int P) { return P > 0 ? align_up(compact_cub_bytes(P), 256) + 256 : 256; }
+
+int lgr_compact_plan(int P, const uint8_t* keep, int32_t* src_row, void* workspace, size_t workspace_bytes, int32_t* rows_out_host,
+                     void* cuda_stream)
+{
+    if (!rows_out_host || P < 0) {
+        g_last_error = "lgr_compact_plan: bad argument";
+        return LGR_ERR_INVALID_ARG;
+    }
+    *rows_out_host = 0;
+    if (P == 0) return LGR_OK;
+    if (!keep || !src_row || !workspace || workspace_bytes < lgr_compact_workspace_bytes(P) || ((uintptr_t)workspace & 255)) {
+        g_last_error = "lgr_compact_plan: missing pointer or workspace smaller than lgr_compact_workspace_bytes(P) / not 256-byte aligned";
+        return LGR_ERR_INVALID_ARG;
+    }
+    cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+    int* d_count = reinterpret_cast<int*>(workspace);
+    size_t cub_bytes = workspace_bytes - 256;
+    {
+        ProfScope ps(ST_COMPACT, stream);
+        LGR_CUDA_TRY(cub::DeviceSelect::Flagged(static_cast<char*>(workspace) + 256, cub_bytes, thrust::counting_iterator<int>(0), keep, src_row,
+                                                d_count, P, stream));
+    }
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    LGR_CUDA_TRY(cudaMemcpyAsync(rows_out_host, d_count, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    LGR_CUDA_TRY(cudaStreamSynchronize(stream));
+    return LGR_OK;
+}
+
+int lgr_compact_rows(int rows_out, const int32_t* src_row, int n_tensors, const lgr_compact_tensor* tensors, void* cuda_stream)
+{
+    if (rows_out < 0 || n_tensors < 0 || n_tensors > CMP_MAX_TENSORS || (n_tensors && !tensors) || (rows_out && !src_row)) {
+        g_last_error = "lgr_compact_rows: bad argument (at most 24 tensors per call)";
+        return LGR_ERR_INVALID_ARG;
+    }
+    if (rows_out == 0 || n_tensors == 0) return LGR_OK;
+    CompactTable t;
+    memset(&t, 0, sizeof(t));
+    long long chunks = 0;
+    int k = 0;
+    for (int i = 0; i < n_tensors; i++) {
+        if (tensors[i].row_words == 0) continue;
+        if (tensors[i].row_words < 0 || !tensors[i].src || !tensors[i].dst) {
+            g_last_error = "lgr_compact_rows: tensor with a missing pointer or negative row width";
+            return LGR_ERR_INVALID_ARG;
+        }
+        t.src[k] = static_cast<const float*>(tensors[i].src);
+        t.dst[k] = static_cast<float*>(tensors[i].dst);
+        t.width[k] = tensors[i].row_words;
+        t.chunk_start[k] = (int)chunks;
+        chunks += ((long long)rows_out * tensors[i].row_words + CMP_CHUNK - 1) / CMP_CHUNK;
+        k++;
+    }
+    if (chunks > 0x7fffffffLL) {
+        g_last_error = "lgr_compact_rows: too many elements for one launch";
+        return LGR_ERR_INVALID_ARG;
+    }
+    for (int i = k; i <= CMP_MAX_TENSORS; i++) t.chunk_start[i] = (int)chunks;
+    t.count = k;
+    t.rows_out = rows_out;
+    if (chunks == 0) return LGR_OK;
+    cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+    {
+        ProfScope ps(ST_COMPACT, stream);
+        compact_gather_kernel<<<(unsigned)chunks, 256, 0, stream>>>(t, src_row);
+    }
+    LGR_LAUNCH_CHECK("compact_gather_kernel", false, stream);
     return LGR_OK;
 }
 

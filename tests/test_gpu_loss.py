@@ -73,7 +73,7 @@ def test_identical_images_and_determinism():
 
 def _torch_ssim(img1, img2):
     """torch restatement of utils/loss_utils.py:45-85 for the full-size check"""
-    g = torch.from_numpy(lo.window_2d()).to(img1.device)
+    g = torch.from_numpy(lo.window_2d()).to(img1.device, img1.dtype)
     C = img1.shape[0]
     w = g.expand(C, 1, 11, 11).contiguous()
     conv = lambda t: F.conv2d(t[None], w, padding=5, groups=C)[0]  # noqa: E731
