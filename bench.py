@@ -35,8 +35,8 @@ UNIT = "views/s"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--P", type=int, default=3_000_000, help="number of Gaussians (default: the 3M workload)")
     ap.add_argument("--width", type=int, default=1920)
@@ -54,6 +54,9 @@ def parse_args():
 # clocks (B200_PROFILING.md recipe), sampled DURING the timed region
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """nvidia-smi polled every 50 ms from construction on; every line is stamped on arrival, and only the lines that arrived
+    between begin() and end() (the timed region, plus -- when that region is shorter than two polls -- an untimed continuation of
+    the same steps, flagged in "window") are reported."""
     Q = "index,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
@@ -61,10 +64,10 @@ class ClockSampler:
         self.idx = gpu_index
         self.lines = []
         self.proc = None
-
-    def start(self):
+        self.t0 = self.t1 = None
+        self.window = "timed region"
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -73,19 +76,28 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def begin(self):
+        self.t0 = time.perf_counter()
+
+    def end(self):
+        self.t1 = time.perf_counter()
+
+    def in_window(self):
+        return [ln for (t, ln) in list(self.lines) if self.t0 is not None and t >= self.t0 and (self.t1 is None or t <= self.t1)]
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        lines = self.in_window()
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        for ln in lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -98,7 +110,7 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "samples": len(sm),
-                "reasons": sorted(reasons)}
+                "reasons": sorted(reasons), "window": self.window}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -175,6 +187,24 @@ def cpu_oracle_sample(scene, cam, W, H):
     o.backward(v, f, dpix, act["means3D"], shs=act["shs"], scales=act["scales"], rotations=act["rotations"])
     dt = time.perf_counter() - t0
     return 1.0 / dt, dt
+
+
+def make_torch_reference_loss(dev):
+    """(1-l)*l1_loss + l*(1-ssim) with l = 0.2 exactly as utils/loss_utils.py:18-85 composes it from torch ops (5 depthwise conv2d +
+    elementwise + autograd): what the reference's training loops launch per iteration (prune_finetune.py:160-164)."""
+    import torch.nn.functional as F
+    g1 = torch.tensor([math.exp(-((k - 5) ** 2) / (2 * 1.5 ** 2)) for k in range(11)], device=dev)
+    g1 = g1 / g1.sum()
+    w2 = (g1[:, None] * g1[None, :]).expand(3, 1, 11, 11).contiguous()
+
+    def torch_loss(x, y):
+        cv = lambda t: F.conv2d(t[None], w2, padding=5, groups=3)[0]  # noqa: E731
+        mu1, mu2 = cv(x), cv(y)
+        s1, s2, s12 = cv(x * x) - mu1 * mu1, cv(y * y) - mu2 * mu2, cv(x * y) - mu1 * mu2
+        m = ((2 * mu1 * mu2 + 1e-4) * (2 * s12 + 9e-4)) / ((mu1 * mu1 + mu2 * mu2 + 1e-4) * (s1 + s2 + 9e-4))
+        return 0.8 * (x - y).abs().mean() + 0.2 * (1.0 - m.mean())
+    return torch_loss
+
 
 
 def main():
@@ -291,14 +321,26 @@ def main():
         barrier()
         torch.cuda.synchronize()
         if sampler:
-            sampler.start()
+            sampler.begin()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for s in range(steps):
             fn(args.warmup + s)
         e1.record()
         torch.cuda.synchronize()
-        clocks = sampler.stop() if sampler else None
+        clocks = None
+        if sampler:
+            sampler.end()
+            if len(sampler.in_window()) < 2 and world == 1:
+                # the timed region was shorter than two polls: keep the GPU under the SAME load (untimed) until 0.4 s have been sampled
+                sampler.window = "timed region + untimed continuation of the same steps (region shorter than two 50 ms polls)"
+                k = 0
+                while time.perf_counter() - sampler.t0 < 0.4:
+                    fn(args.warmup + steps + k)
+                    k += 1
+                torch.cuda.synchronize()
+                sampler.end()
+            clocks = sampler.stop()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
@@ -317,11 +359,12 @@ def main():
         return 0
 
     # ---------------- warm-up, then the timed regions ----------------
+    sampler = ClockSampler(local) if rank == 0 else None      # starts polling now: nvidia-smi needs ~0.2 s to come up
     for s in range(args.warmup):
         step_resident(s)
     torch.cuda.synchronize()
     n0 = capi.launch_count() if args.impl == "ours" else 0
-    ms, clocks = timed(step_resident, args.steps, ClockSampler(local) if rank == 0 else None)
+    ms, clocks = timed(step_resident, args.steps, sampler)
     launches = (capi.launch_count() - n0) if args.impl == "ours" else 0
     views = args.steps * world
     value = views / (ms * 1e-3)
@@ -407,19 +450,9 @@ def main():
     loss_pass = None
     if args.impl == "ours" and not args.no_roofline and world == 1:
         from lightgaussian_b200 import loss as fused_loss
-        import torch.nn.functional as F
         gimg = torch.rand(3, H, W, device=dev)
         gtgt = torch.rand(3, H, W, device=dev)
-        g1 = torch.tensor([math.exp(-((k - 5) ** 2) / (2 * 1.5 ** 2)) for k in range(11)], device=dev)
-        g1 = g1 / g1.sum()
-        w2 = (g1[:, None] * g1[None, :]).expand(3, 1, 11, 11).contiguous()
-
-        def torch_loss(x, y):                      # op-for-op what utils/loss_utils.py launches (5 conv2d + elementwise + autograd)
-            cv = lambda t: F.conv2d(t[None], w2, padding=5, groups=3)[0]  # noqa: E731
-            mu1, mu2 = cv(x), cv(y)
-            s1, s2, s12 = cv(x * x) - mu1 * mu1, cv(y * y) - mu2 * mu2, cv(x * y) - mu1 * mu2
-            m = ((2 * mu1 * mu2 + 1e-4) * (2 * s12 + 9e-4)) / ((mu1 * mu1 + mu2 * mu2 + 1e-4) * (s1 + s2 + 9e-4))
-            return 0.8 * (x - y).abs().mean() + 0.2 * (1.0 - m.mean())
+        torch_loss = make_torch_reference_loss(dev)
 
         def run(fn):
             def step(_s):
@@ -434,6 +467,39 @@ def main():
         loss_pass = {"fused_ms": t_f, "torch_composed_ms": t_t, "image": [3, H, W],
                      "alg_bytes": 3 * H * W * 4 * (2 + 3 + 2 + 3 + 1),
                      "what": "l1_ssim_loss forward+backward (lgr_image_loss_forward/backward) vs the reference's torch op sequence"}
+
+    # ---------------- whole training iteration (rows N2 + N3 included): render -> L1+DSSIM -> backward -> AdamW -> zero_grad ------
+    # prune_finetune.py:144-166,287-289.  Reported beside the headline (whose step definition stays render+L1+backward).
+    iteration_pass = None
+    if world == 1 and not args.no_roofline:
+        names = ["_xyz", "_features_dc", "_features_rest", "_opacity", "_scaling", "_rotation"]
+        lrs = [1.6e-4, 2.5e-3, 2.5e-3 / 20, 0.05, 0.005, 0.001]                       # arguments/__init__.py OptimizationParams
+        groups = lambda: [{"params": [getattr(pc, n)], "lr": lr, "name": n} for n, lr in zip(names, lrs)]  # noqa: E731
+        torch_loss = make_torch_reference_loss(dev)
+
+        def make_iter(loss_fn, opt):
+            def it(step):
+                i = view_index(step)
+                img = render_fn(cams[i], pc, pipe, bg)["render"]
+                loss_fn(img, targets_dev[i % len(targets_dev)]).backward()
+                opt.step()
+                opt.zero_grad(set_to_none=True)
+            return it
+        zero_grads()
+        arms = {"torch_loss_and_adamw": (torch_loss, torch.optim.AdamW(groups(), lr=0.0, eps=1e-15))}
+        if args.impl == "ours":
+            from lightgaussian_b200 import loss as fused_loss, optim as fused_optim
+            arms["fused_loss_and_adamw"] = (lambda x, y: fused_loss.l1_ssim_loss(x, y, 0.2), fused_optim.FusedAdamW(groups(), lr=0.0, eps=1e-15))
+        iteration_pass = {"what": "render + (0.8 L1 + 0.2 DSSIM) + backward + AdamW.step + zero_grad, iterations/s", "unit": "iterations/s"}
+        nit = min(args.steps, 10)
+        for name, (lf, opt) in arms.items():
+            fn = make_iter(lf, opt)
+            for s_ in range(3):
+                fn(s_)
+            t_it, _ = timed(fn, nit)
+            iteration_pass[name] = nit / (t_it * 1e-3)
+            del opt
+        zero_grads()
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -478,6 +544,8 @@ def main():
             line["significance_pass"] = signif
         if loss_pass:
             line["loss_pass"] = loss_pass
+        if iteration_pass:
+            line["iteration_pass"] = iteration_pass
         if cpu_baseline:
             line["cpu_baseline"] = cpu_baseline
         print(json.dumps(line))

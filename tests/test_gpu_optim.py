@@ -2,6 +2,7 @@
 parameters and both moments, over many steps with the reference's six-group configuration -- against the numpy oracle and
 the torch-CPU golden; fused prune compaction (lgr_compact_plan / lgr_compact_rows) against boolean indexing, and
 `optim.prune_points` against the reference's GaussianModel.prune_points surgery restated with torch ops."""
+import copy
 import os
 
 import numpy as np
@@ -90,9 +91,10 @@ def test_state_dict_round_trip_and_unaligned_views():
             p1[k].grad = gr
         o1.step()
     p2, o2 = _make(FusedAdamW, {k: v.detach().cpu() for k, v in p1.items()})
-    o2.load_state_dict(o1.state_dict())                      # GaussianModel.restore (scene/gaussian_model.py:86-96)
+    # GaussianModel.restore (scene/gaussian_model.py:86-96); deep copies: load_state_dict aliases tensors that need no cast
+    o2.load_state_dict(copy.deepcopy(o1.state_dict()))
     pr, orf = _make(torch.optim.AdamW, {k: v.detach().cpu() for k, v in p1.items()})
-    orf.load_state_dict(o1.state_dict())
+    orf.load_state_dict(copy.deepcopy(o1.state_dict()))
     gr = _grads(333, 99, 9)
     for k in NAMES:
         p2[k].grad = gr[k].clone()
@@ -142,9 +144,10 @@ def _model(P, cls, with_state):
     m.optimizer = opt
     for k, a in zip(NAMES, ["_xyz", "_features_dc", "_features_rest", "_opacity", "_scaling", "_rotation"]):
         setattr(m, a, params[k])
-    m.xyz_gradient_accum = torch.rand(P, 1, device="cuda")
-    m.denom = torch.rand(P, 1, device="cuda")
-    m.max_radii2D = torch.rand(P, device="cuda")
+    gen = torch.Generator().manual_seed(17)
+    m.xyz_gradient_accum = torch.rand(P, 1, generator=gen).cuda()
+    m.denom = torch.rand(P, 1, generator=gen).cuda()
+    m.max_radii2D = torch.rand(P, generator=gen).cuda()
     if with_state:
         for it in range(2):
             for k, gr in _grads(P, it, 13).items():
