@@ -139,3 +139,41 @@ def prune_points(gaussians, mask):
         setattr(gaussians, _GROUP_ATTR[group["name"]], new)
     for n in aux_names:
         setattr(gaussians, n, next(outs))
+
+
+def to_fused(optimizer):
+    """A FusedAdamW over the SAME parameter tensors, groups (incl. "name" and the current lr) and hyper-parameters as an existing
+    torch.optim.AdamW, carrying its state over."""
+    if isinstance(optimizer, FusedAdamW):
+        return optimizer
+    if type(optimizer) is not torch.optim.AdamW:
+        raise TypeError(f"to_fused expects torch.optim.AdamW, got {type(optimizer).__name__}")
+    skip = {"foreach", "fused", "capturable", "differentiable", "maximize", "amsgrad", "decoupled_weight_decay"}
+    for g in optimizer.param_groups:
+        if g.get("amsgrad") or g.get("maximize") or g.get("capturable") or g.get("differentiable"):
+            raise NotImplementedError("to_fused: amsgrad / maximize / capturable / differentiable groups are not supported")
+    groups = [{k: v for k, v in g.items() if k not in skip} for g in optimizer.param_groups]
+    fused = FusedAdamW(groups, **{k: v for k, v in optimizer.defaults.items() if k not in skip})
+    for p, st in optimizer.state.items():
+        fused.state[p] = st
+    return fused
+
+
+def install(GaussianModel):
+    """Make a GaussianModel class (scene/gaussian_model.py) use the fused optimizer step and prune compaction without editing it:
+    `training_setup` (:176-224) is wrapped so that the AdamW it builds is replaced by an equivalent FusedAdamW, and `prune_points`
+    (:587-600) becomes `optim.prune_points`.  Idempotent."""
+    if getattr(GaussianModel, "_lgr_fused_optim", False):
+        return GaussianModel
+    original_setup = GaussianModel.training_setup
+
+    def training_setup(self, *args, **kwargs):
+        out = original_setup(self, *args, **kwargs)
+        self.optimizer = to_fused(self.optimizer)
+        return out
+
+    training_setup.__wrapped__ = original_setup
+    GaussianModel.training_setup = training_setup
+    GaussianModel.prune_points = prune_points
+    GaussianModel._lgr_fused_optim = True
+    return GaussianModel

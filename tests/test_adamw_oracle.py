@@ -51,3 +51,30 @@ def test_fused_adamw_keeps_the_reference_facing_surface():
         opt.step()
     with pytest.raises(NotImplementedError):
         FusedAdamW([p], amsgrad=True)
+
+
+def test_install_swaps_optimizer_and_prune_on_a_gaussian_model_class():
+    from lightgaussian_b200 import optim
+
+    class FakeModel:                                     # the two methods of scene/gaussian_model.py that install() touches
+        def training_setup(self, training_args):
+            self._xyz = torch.nn.Parameter(torch.zeros(5, 3))
+            self._opacity = torch.nn.Parameter(torch.zeros(5, 1))
+            self.optimizer = torch.optim.AdamW([{"params": [self._xyz], "lr": 1e-4 * training_args, "name": "xyz"},
+                                                {"params": [self._opacity], "lr": 0.05, "name": "opacity"}], lr=0.0, eps=1e-15)
+            return "ret"
+
+        def prune_points(self, mask):
+            raise AssertionError("replaced")
+
+    optim.install(FakeModel)
+    optim.install(FakeModel)                             # idempotent
+    m = FakeModel()
+    assert m.training_setup(2.0) == "ret"
+    assert isinstance(m.optimizer, optim.FusedAdamW)
+    assert [g["name"] for g in m.optimizer.param_groups] == ["xyz", "opacity"]
+    assert m.optimizer.param_groups[0]["lr"] == 2e-4 and m.optimizer.param_groups[0]["eps"] == 1e-15
+    assert m.optimizer.param_groups[0]["params"][0] is m._xyz
+    assert FakeModel.prune_points is optim.prune_points
+    with pytest.raises(TypeError):
+        optim.to_fused(torch.optim.SGD([m._xyz], lr=0.1))

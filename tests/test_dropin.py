@@ -52,6 +52,8 @@ g = GM(3)
 assert g.scaling_activation is torch.exp and g.opacity_activation is torch.sigmoid
 assert g.rotation_activation is torch.nn.functional.normalize
 from arguments import PipelineParams
+from lightgaussian_b200 import optim
+assert GM.prune_points is optim.prune_points and GM.training_setup.__wrapped__ is not None     # row N3 installed by the drop-in
 print("ok")
 """ % (os.path.join(ROOT, "dropin"), os.path.join(ROOT, "dropin"))
     env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(ROOT, "dropin"), ROOT, REF]))
