@@ -498,6 +498,26 @@ def main():
                 fn(s_)
             t_it, _ = timed(fn, nit)
             iteration_pass[name] = nit / (t_it * 1e-3)
+            if name == "fused_loss_and_adamw":
+                # device time of the N2/N3 kernels inside this iteration (library CUDA events), against the HBM peak
+                peak_rows = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]) \
+                    if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+                capi.profile_collect()
+                capi.profile_enable(True)
+                for s_ in range(5):
+                    fn(s_)
+                prof_rows = capi.profile_collect()
+                capi.profile_enable(False)
+                n_el = sum(getattr(pc, n).numel() for n in names)
+                alg_rows = {"adamw_multi_kernel": 28 * n_el, "image_loss_forward_kernel": 3 * H * W * 20,
+                            "image_loss_backward_kernel": 3 * H * W * 24}
+                rows = {}
+                for kname, (ms_tot, nl) in prof_rows.items():
+                    if kname in alg_rows and nl:
+                        ms1 = ms_tot / nl
+                        rows[kname] = {"ms_per_launch": ms1, "alg_bytes": alg_rows[kname], "gbs": alg_rows[kname] / (ms1 * 1e-3) / 1e9,
+                                       "frac_of_hbm_peak": alg_rows[kname] / (ms1 * 1e-3) / 1e9 / peak_rows}
+                iteration_pass["kernels"] = rows
             del opt
         zero_grads()
 
