@@ -1,7 +1,12 @@
 """Workload for the ncu capture of the N2/N3 kernels (run under `ncu -k regex:image_loss|adamw_multi|compact_gather`):
 fused loss forward+backward on one 3x1080x1920 image, one FusedAdamW step over the six groups of a 3M-Gaussian model, one prune
 compaction (66 %) of parameters + both moments."""
+import os
+import sys
+
 import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 from lightgaussian_b200 import loss as fused_loss
 from lightgaussian_b200.optim import FusedAdamW, compact_rows

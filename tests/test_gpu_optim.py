@@ -61,6 +61,59 @@ def test_bit_exact_against_torch_adamw(P):
         assert float(ours.state[ours_p[k]]["step"]) == float(ref.state[ref_p[k]]["step"]) == 25.0
 
 
+@pytest.mark.parametrize("scale", [1e-18, 1e-21, 1e30])
+def test_bit_exact_on_zeros_denormals_and_extremes(scale):
+    """faint gradients: g*g underflows to denormals / zero, exp_avg_sq becomes denormal, the quotient m/d spans the whole exponent
+    range -- the operands that take the fp64 route inside the kernel (and the IEEE slow path inside torch's)."""
+    P = 30011
+    init = _groups(P, 5)
+    ours_p, ours = _make(FusedAdamW, init)
+    ref_p, ref = _make(torch.optim.AdamW, init)
+    for it in range(6):
+        gr = _grads(P, it, 21)
+        for k in NAMES:
+            g = gr[k] * scale if it != 3 else torch.zeros_like(gr[k])        # one step with exact zeros everywhere
+            ours_p[k].grad = g.clone()
+            ref_p[k].grad = g.clone()
+        ours.step()
+        ref.step()
+    for k in NAMES:
+        assert torch.equal(ours_p[k], ref_p[k]), k
+        assert torch.equal(ours.state[ours_p[k]]["exp_avg"], ref.state[ref_p[k]]["exp_avg"]), k
+        assert torch.equal(ours.state[ours_p[k]]["exp_avg_sq"], ref.state[ref_p[k]]["exp_avg_sq"]), k
+
+
+def test_bit_exact_when_the_quotient_is_subnormal():
+    """first moments that have decayed for hundreds of steps against second moments that have not: m/d lands in the subnormal
+    range (the lanes that take the exact binary64 route), with parameters small enough for those bits to show."""
+    P = 20000
+    g = torch.Generator().manual_seed(3)
+    init = {k: torch.randn((P,) + SHAPES[k], generator=g) * 1e-40 for k in NAMES}
+    ours_p, ours = _make(FusedAdamW, init)
+    ref_p, ref = _make(torch.optim.AdamW, init)
+    zero = {k: torch.zeros((P,) + SHAPES[k]).cuda() for k in NAMES}
+    for opt, prm in ((ours, ours_p), (ref, ref_p)):
+        for k in NAMES:
+            prm[k].grad = zero[k].clone()
+        opt.step()                                            # creates the state
+    for k in NAMES:
+        expo = torch.rand((P,) + SHAPES[k], generator=g) * 20 - 46                      # |m| from 1e-46 (flushes to 0) to 1e-26
+        m = (torch.randn((P,) + SHAPES[k], generator=g).sign() * 10.0 ** expo).float().cuda()
+        v = (10.0 ** (torch.rand((P,) + SHAPES[k], generator=g) * 8 - 6)).float().cuda()   # 1e-6 .. 1e2
+        for opt, prm in ((ours, ours_p), (ref, ref_p)):
+            opt.state[prm[k]]["exp_avg"].copy_(m)
+            opt.state[prm[k]]["exp_avg_sq"].copy_(v)
+    for it in range(3):
+        for opt, prm in ((ours, ours_p), (ref, ref_p)):
+            for k in NAMES:
+                prm[k].grad = zero[k].clone()
+            opt.step()
+    for k in NAMES:
+        assert torch.equal(ours_p[k], ref_p[k]), k
+        assert torch.equal(ours.state[ours_p[k]]["exp_avg"], ref.state[ref_p[k]]["exp_avg"]), k
+        assert float(ours_p[k].abs().max()) > 0
+
+
 def test_against_oracle_and_torch_cpu_golden():
     g = np.load(GOLD)
     params = {k: torch.nn.Parameter(torch.from_numpy(g[f"p0_{k}"]).cuda()) for k in NAMES}
