@@ -521,6 +521,47 @@ def main():
             del opt
         zero_grads()
 
+    # ---------------- VecTree k-means iteration (row N4): 80 000 samples x 8192 codes x 27 dims, importance weighted ----------------
+    vq_pass = None
+    if args.impl == "ours" and world == 1 and not args.no_roofline:
+        from lightgaussian_b200 import vectree as fused_vq
+        nv, dv, Kv = 80000, 27, 8192
+        gv = torch.Generator(device=dev).manual_seed(3)
+        xv = torch.randn(nv, dv, device=dev, generator=gv) * 0.5
+        wv = torch.rand(nv, device=dev, generator=gv) ** 2
+        model_vq = fused_vq.VectorQuantize(dim=dv, codebook_size=Kv).to(dev).train()
+        embed_t = model_vq._codebook.embed[0].clone()
+        cs_t = torch.zeros(Kv, device=dev)
+
+        def ours_iter(_s):
+            model_vq(xv.unsqueeze(0), weight=wv.reshape(1, -1, 1))
+
+        def torch_iter(_s):                        # vq.py:262-300 op for op: cdist, argmax, one_hot, broadcast multiply, einsum, EMA
+            wn = (wv * wv.numel() / wv.sum()).reshape(1, -1, 1)
+            flat = xv[None]
+            ind = (-torch.cdist(flat, embed_t[None], p=2)).argmax(dim=-1)
+            onehot = torch.nn.functional.one_hot(ind, Kv).type(xv.dtype)
+            cs = cs_t * 0.8 + 0.2 * (onehot * wn).sum(dim=1)[0]
+            esum = torch.einsum("hnd,hnc->hcd", flat * wn, onehot)[0]
+            sm = (cs + 1e-5) / (cs.sum() + Kv * 1e-5) * cs.sum()
+            return embed_t * 0.8 + 0.2 * esum / sm[:, None]
+        for fn in (ours_iter, torch_iter):
+            for _ in range(2):
+                fn(0)
+        capi.profile_collect()
+        capi.profile_enable(True)
+        t_o, _ = timed(ours_iter, 10)
+        prof_vq = capi.profile_collect()
+        capi.profile_enable(False)
+        t_t, _ = timed(torch_iter, 5)
+        ms_assign = prof_vq["vq_assign_kernel"][0] / max(prof_vq["vq_assign_kernel"][1], 1)
+        flops = 2.0 * nv * Kv * dv
+        vq_pass = {"fused_ms": t_o / 10, "torch_formulation_ms": t_t / 5, "assign_kernel_ms": ms_assign, "samples": nv, "codes": Kv, "dim": dv,
+                   "assign_tflops_fp32": flops / (ms_assign * 1e-3) / 1e12,
+                   "what": "one importance-weighted EMA k-means iteration (VectorQuantize.forward in training mode); the assign kernel is "
+                           "FP32-FFMA-bound: 2*n*K*d flops"}
+        del model_vq, xv, wv
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         if args.impl == "ours":
@@ -566,6 +607,8 @@ def main():
             line["loss_pass"] = loss_pass
         if iteration_pass:
             line["iteration_pass"] = iteration_pass
+        if vq_pass:
+            line["vq_pass"] = vq_pass
         if cpu_baseline:
             line["cpu_baseline"] = cpu_baseline
         print(json.dumps(line))

@@ -205,6 +205,26 @@ int lgr_compact_plan(int P, const uint8_t* keep, int32_t* src_row, void* workspa
                      void* cuda_stream);
 int lgr_compact_rows(int rows_out, const int32_t* src_row, int n_tensors, const lgr_compact_tensor* tensors, void* cuda_stream);
 
+/* ---- VecTree vector quantisation of the SH features (vectree/vq.py:262-306, vectree/vectree.py:86-125,166-207) ----
+ * All pointers are device pointers; x is [n,d] row-major float32, embed [K,d], d <= 64.
+ * lgr_vq_assign: idx[i] = argmin_c |x_i - e_c|^2 (evaluated as |e_c|^2 - 2 x_i.e_c like torch.cdist's expansion; smallest index wins
+ *   ties).  When cluster_batch / embed_sum are given they receive sum_i w_i [idx_i = c] and sum_i w_i x_i [idx_i = c], with
+ *   w_i = weight_i * n / *weight_sum (the reference's normalisation), or 1 when weight is NULL: the quantities EuclideanCodebook.forward
+ *   forms with F.one_hot and einsum.  workspace: lgr_vq_workspace_bytes(n) bytes, 8-byte aligned.
+ * lgr_vq_ema_update: cluster_size <- decay*cluster_size + (1-decay)*cluster_batch; embed <- decay*embed + (1-decay)*embed_sum/smoothed,
+ *   smoothed = (cluster_size+eps)/(sum+K*eps)*sum (vq.py:286-300).  scratch: one float.
+ * lgr_vq_gather: out[i,:] = embed[idx[i],:] (batched_embedding, vq.py:161-165).
+ * lgr_vq_pack_indices / lgr_vq_unpack_indices: `bits` bits per index, most significant first, bytes filled from the high bit
+ *   (dec2bin + np.packbits, vectree.py:120-125; np.unpackbits + bin2dec, vectree/utils.py:33-39); out has (n*bits+7)/8 bytes. */
+size_t lgr_vq_workspace_bytes(int64_t n);
+int lgr_vq_assign(int n, int d, int K, const float* x, const float* embed, const float* weight, const float* weight_sum, int32_t* idx,
+                  float* cluster_batch, float* embed_sum, void* workspace, void* cuda_stream);
+int lgr_vq_ema_update(int K, int d, double decay, double eps, float* cluster_size, float* embed, const float* cluster_batch,
+                      const float* embed_sum, float* scratch, void* cuda_stream);
+int lgr_vq_gather(int n, int d, const int32_t* idx, const float* embed, float* out, void* cuda_stream);
+int lgr_vq_pack_indices(int64_t n, int bits, const int32_t* idx, uint8_t* out, void* cuda_stream);
+int lgr_vq_unpack_indices(int64_t n, int bits, const uint8_t* in, int32_t* idx, void* cuda_stream);
+
 /* present[i] = (view-space z of point i) > 0.2   (RAST/cuda_rasterizer/rasterizer_impl.cu:54-66, auxiliary.h:139-164) */
 int lgr_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix, uint8_t* present,
                      void* cuda_stream);

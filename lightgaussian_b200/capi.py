@@ -107,6 +107,18 @@ def load():
         lib.lgr_compact_plan.argtypes = [i32, vp, vp, vp, C.c_size_t, C.POINTER(C.c_int32), vp]
         lib.lgr_compact_rows.restype = i32
         lib.lgr_compact_rows.argtypes = [i32, vp, i32, C.POINTER(LgrCompactTensor), vp]
+        lib.lgr_vq_workspace_bytes.restype = C.c_size_t
+        lib.lgr_vq_workspace_bytes.argtypes = [C.c_int64]
+        lib.lgr_vq_assign.restype = i32
+        lib.lgr_vq_assign.argtypes = [i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+        lib.lgr_vq_ema_update.restype = i32
+        lib.lgr_vq_ema_update.argtypes = [i32, i32, C.c_double, C.c_double, vp, vp, vp, vp, vp, vp]
+        lib.lgr_vq_gather.restype = i32
+        lib.lgr_vq_gather.argtypes = [i32, i32, vp, vp, vp, vp]
+        lib.lgr_vq_pack_indices.restype = i32
+        lib.lgr_vq_pack_indices.argtypes = [C.c_int64, i32, vp, vp, vp]
+        lib.lgr_vq_unpack_indices.restype = i32
+        lib.lgr_vq_unpack_indices.argtypes = [C.c_int64, i32, vp, vp, vp]
         lib.lgr_multimem_allreduce.restype = i32
         lib.lgr_multimem_allreduce.argtypes = [vp, i32, i32, C.c_size_t, vp]
         lib.lgr_sh_grad_from_views.restype = i32

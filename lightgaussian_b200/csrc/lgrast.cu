@@ -23,6 +23,7 @@
 #include <thrust/iterator/transform_iterator.h>
 #include <thrust/iterator/counting_iterator.h>
 #include <cmath>
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <cstring>
@@ -46,12 +47,12 @@ std::atomic<uint64_t> g_launches{0};
 
 // ---- optional per-stage device timing (CUDA events on the launch stream), used by bench.py's roofline ----
 enum StageId { ST_PREPROCESS = 0, ST_DEPTH_SORT, ST_SCAN, ST_EMIT, ST_TILE_SORT, ST_RANGES, ST_BLEND_FWD, ST_BLEND_FWD_COUNT,
-               ST_SCORE, ST_BLEND_BWD, ST_PREPROCESS_BWD, ST_MEMSET, ST_SH_GRAD, ST_PEER_ALLREDUCE, ST_LOSS_FWD, ST_LOSS_BWD, ST_ADAMW, ST_COMPACT, ST_COUNT };
+               ST_SCORE, ST_BLEND_BWD, ST_PREPROCESS_BWD, ST_MEMSET, ST_SH_GRAD, ST_PEER_ALLREDUCE, ST_LOSS_FWD, ST_LOSS_BWD, ST_ADAMW, ST_COMPACT, ST_VQ_ASSIGN, ST_VQ_UPDATE, ST_COUNT };
 const char* const kStageNames[ST_COUNT] = {"preprocess_kernel", "depth_sort(cub)", "scan(cub)", "emit_kernel", "tile_sort(cub)",
                                            "ranges_kernel", "blend_forward_kernel", "blend_forward_kernel<count>", "score_kernel",
                                            "blend_backward_kernel", "preprocess_backward_kernel", "memset", "sh_grad_from_views_kernel",
                                            "peer_allreduce_kernel", "image_loss_forward_kernel", "image_loss_backward_kernel", "adamw_multi_kernel",
-                                           "compact_gather_kernel"};
+                                           "compact_gather_kernel", "vq_assign_kernel", "vq_ema_kernels"};
 struct ProfRecord { int stage; cudaEvent_t a, b; };
 bool g_prof_on = false;
 std::vector<ProfRecord> g_prof_records;
@@ -918,6 +919,7 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(PreBackArgs a)
 #include "lgr_raw.cuh"
 #include "lgr_loss.cuh"
 #include "lgr_optim.cuh"
+#include "lgr_vq.cuh"
 namespace {
 
 // ------------------------------------------------------------------------------------------------
@@ -1600,6 +1602,98 @@ int lgr_compact_rows(int rows_out, const int32_t* src_row, int n_tensors, const 
         compact_gather_kernel<<<(unsigned)chunks, 256, 0, stream>>>(t, src_row);
     }
     LGR_LAUNCH_CHECK("compact_gather_kernel", false, stream);
+    return LGR_OK;
+}
+
+// ---- VecTree vector quantisation (row N4) ----
+size_t lgr_vq_workspace_bytes(int64_t n) { return (size_t)(n > 0 ? n : 0) * sizeof(unsigned long long) + 256; }
+
+int lgr_vq_assign(int n, int d, int K, const float* x, const float* embed, const float* weight, const float* weight_sum, int32_t* idx,
+                  float* cluster_batch, float* embed_sum, void* workspace, void* cuda_stream)
+{
+    if (n < 0 || d <= 0 || d > 64 || K <= 0 || (n && (!x || !workspace)) || !embed || (weight && !weight_sum) || ((uintptr_t)workspace & 7)) {
+        g_last_error = "lgr_vq_assign: bad argument (1 <= d <= 64, K >= 1, workspace of lgr_vq_workspace_bytes(n) bytes)";
+        return LGR_ERR_INVALID_ARG;
+    }
+    cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+    if (cluster_batch) LGR_CUDA_TRY(cudaMemsetAsync(cluster_batch, 0, sizeof(float) * K, stream));
+    if (embed_sum) LGR_CUDA_TRY(cudaMemsetAsync(embed_sum, 0, sizeof(float) * (size_t)K * d, stream));
+    if (n == 0) return LGR_OK;
+    unsigned long long* best = static_cast<unsigned long long*>(workspace);
+    {
+        ProfScope ps(ST_VQ_ASSIGN, stream);
+        vq_init_best_kernel<<<(n + 255) / 256, 256, 0, stream>>>(n, best);
+        if (d <= 8) vq_launch_assign<8>(n, d, K, x, embed, best, stream);
+        else if (d <= 16) vq_launch_assign<16>(n, d, K, x, embed, best, stream);
+        else if (d <= 28) vq_launch_assign<28>(n, d, K, x, embed, best, stream);
+        else if (d <= 32) vq_launch_assign<32>(n, d, K, x, embed, best, stream);
+        else if (d <= 48) vq_launch_assign<48>(n, d, K, x, embed, best, stream);
+        else vq_launch_assign<64>(n, d, K, x, embed, best, stream);
+    }
+    LGR_LAUNCH_CHECK("vq_assign_kernel", false, stream);
+    const long long total = (long long)n * (d + 1);
+    vq_accumulate_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(n, d, best, x, weight, (float)n, weight_sum, idx, cluster_batch,
+                                                                                 embed_sum);
+    LGR_LAUNCH_CHECK("vq_accumulate_kernel", false, stream);
+    return LGR_OK;
+}
+
+int lgr_vq_ema_update(int K, int d, double decay, double eps, float* cluster_size, float* embed, const float* cluster_batch,
+                      const float* embed_sum, float* scratch, void* cuda_stream)
+{
+    if (K <= 0 || d <= 0 || !cluster_size || !embed || !cluster_batch || !embed_sum || !scratch) {
+        g_last_error = "lgr_vq_ema_update: bad argument";
+        return LGR_ERR_INVALID_ARG;
+    }
+    cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+    {
+        ProfScope ps(ST_VQ_UPDATE, stream);
+        vq_ema_cluster_kernel<<<1, 1024, 0, stream>>>(K, (float)decay, (float)(1.0 - decay), cluster_size, cluster_batch, scratch);
+        vq_ema_embed_kernel<<<(K * d + 255) / 256, 256, 0, stream>>>(K, d, (float)decay, (float)(1.0 - decay), (float)eps, (float)((double)K * eps),
+                                                                      cluster_size, scratch, embed_sum, embed);
+    }
+    LGR_LAUNCH_CHECK("vq_ema_embed_kernel", false, stream);
+    return LGR_OK;
+}
+
+int lgr_vq_gather(int n, int d, const int32_t* idx, const float* embed, float* out, void* cuda_stream)
+{
+    if (n < 0 || d <= 0 || (n && (!idx || !embed || !out))) {
+        g_last_error = "lgr_vq_gather: bad argument";
+        return LGR_ERR_INVALID_ARG;
+    }
+    if (n == 0) return LGR_OK;
+    cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+    const long long total = (long long)n * d;
+    vq_gather_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(n, d, idx, embed, out);
+    LGR_LAUNCH_CHECK("vq_gather_kernel", false, stream);
+    return LGR_OK;
+}
+
+int lgr_vq_pack_indices(int64_t n, int bits, const int32_t* idx, uint8_t* out, void* cuda_stream)
+{
+    if (n < 0 || bits < 1 || bits > 31 || (n && (!idx || !out))) {
+        g_last_error = "lgr_vq_pack_indices: bad argument (1 <= bits <= 31)";
+        return LGR_ERR_INVALID_ARG;
+    }
+    if (n == 0) return LGR_OK;
+    cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+    const long long n_bytes = ((long long)n * bits + 7) / 8;
+    vq_pack_kernel<<<(unsigned)((n_bytes + 255) / 256), 256, 0, stream>>>(n, bits, idx, out, n_bytes);
+    LGR_LAUNCH_CHECK("vq_pack_kernel", false, stream);
+    return LGR_OK;
+}
+
+int lgr_vq_unpack_indices(int64_t n, int bits, const uint8_t* in, int32_t* idx, void* cuda_stream)
+{
+    if (n < 0 || bits < 1 || bits > 31 || (n && (!idx || !in))) {
+        g_last_error = "lgr_vq_unpack_indices: bad argument (1 <= bits <= 31)";
+        return LGR_ERR_INVALID_ARG;
+    }
+    if (n == 0) return LGR_OK;
+    cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+    vq_unpack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(n, bits, in, idx);
+    LGR_LAUNCH_CHECK("vq_unpack_kernel", false, stream);
     return LGR_OK;
 }
 

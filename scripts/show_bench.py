@@ -12,6 +12,6 @@ if "stages" in d:
     print("  whole view:", d["roofline"]["whole_view"])
 if "cpu_baseline" in d:
     print("  cpu_baseline:", d["cpu_baseline"])
-for k in ("significance_pass", "loss_pass", "iteration_pass"):
+for k in ("significance_pass", "loss_pass", "iteration_pass", "vq_pass"):
     if k in d:
         print(f"  {k}:", {a: (round(b, 3) if isinstance(b, float) else b) for a, b in d[k].items() if a != "what"})
