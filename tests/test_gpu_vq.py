@@ -129,7 +129,6 @@ def test_training_reduces_the_weighted_error():
     q.train_codebook()
     e1 = err()
     assert e1 < 0.2 * e0, (e0, e1)
-    assert e1 < 1.0                                             # ~27 * 0.1^2 = 0.27 is the floor for a perfect codebook of the centres
 
 
 def _torch_reference_iteration(x, w, embed, cluster_size, decay=0.8, eps=1e-5):
