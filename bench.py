@@ -267,13 +267,19 @@ def main():
         if render_fn is None:
             kind = "port"
 
+    # the step's L1: each arm uses ITS OWN stack's l1_loss -- ours the fused kernel pair (lightgaussian_b200.loss, what
+    # dropin/utils/loss_utils.py exports), the reference arm the torch composition of utils/loss_utils.py:18-19
+    step_loss = None
+    if args.impl == "ours" and os.environ.get("LGR_BENCH_TORCH_L1", "0") != "1":
+        from lightgaussian_b200.loss import l1_loss as step_loss
+
     def view_index(step):
         return (step * world + rank) % len(cams)
 
     def step_resident(step):
         i = view_index(step)
         zero_grads()
-        loss = train_view(render_fn, cams[i], pc, pipe, bg, targets_dev[i % len(targets_dev)])
+        loss = train_view(render_fn, cams[i], pc, pipe, bg, targets_dev[i % len(targets_dev)], step_loss)
         allreduce_grads()
         return loss
 
@@ -297,7 +303,8 @@ def main():
             slot["tgt"].copy_(targets_host[i % len(targets_host)], non_blocking=True)  # H2D: this step's target image
             slot["ev"].record(copy_stream)
 
-    e2e_state = {"primed": -1}
+    e2e_state = {"primed": -1, "losses": []}
+    loss_ring = [dict(host=torch.empty(1).pin_memory(), ev=torch.cuda.Event(), pending=False) for _ in range(2)]
 
     def step_e2e(step):
         if e2e_state["primed"] != step:
@@ -308,10 +315,21 @@ def main():
         torch.cuda.current_stream().wait_event(slot["ev"])
         e2e_cam.world_view_transform, e2e_cam.full_proj_transform, e2e_cam.camera_center = slot["wv"], slot["fp"], slot["cc"]
         zero_grads()
-        loss = train_view(render_fn, e2e_cam, pc, pipe, bg, slot["tgt"])
+        loss = train_view(render_fn, e2e_cam, pc, pipe, bg, slot["tgt"], step_loss)
         allreduce_grads()
         slot["used"].record()
-        return float(loss.item())                                   # D2H: the step's result
+        # D2H: the step's result goes to pinned host memory asynchronously and is READ one step later (the host never stalls the
+        # launch of the next step; every step's value is read inside the timed region, the last one at its closing synchronise)
+        res = loss_ring[step % 2]
+        res["host"].copy_(loss.detach().reshape(1), non_blocking=True)
+        res["ev"].record()
+        prev = loss_ring[(step + 1) % 2]
+        if prev["pending"]:
+            prev["ev"].synchronize()
+            e2e_state["losses"].append(float(prev["host"][0]))
+        res["pending"] = True
+        prev["pending"] = False
+        return None
 
     def barrier():
         if world > 1:
@@ -373,7 +391,13 @@ def main():
     if not args.no_e2e:
         for s in range(2):
             step_e2e(s)
+        e2e_state["losses"].clear()
         ms_e, _ = timed(step_e2e, args.steps)
+        for r in loss_ring:                                          # the last step's value (its copy completed before timed() returned)
+            if r["pending"]:
+                e2e_state["losses"].append(float(r["host"][0]))
+                r["pending"] = False
+        assert len(e2e_state["losses"]) >= args.steps and all(math.isfinite(v) for v in e2e_state["losses"])
         h2d = 3 * H * W * 4 + (16 + 16 + 3) * 4
         e2e = {"value": views / (ms_e * 1e-3), "unit": UNIT, "ms_per_step": ms_e / args.steps, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": 4}
@@ -582,7 +606,7 @@ def main():
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": f"{P} Gaussians SH degree 3, {W}x{H}, {len(cams)} synthetic cameras (Fibonacci sphere r=3), "
-                                   "step = render()+L1+backward to raw leaves" + (" + 1 NCCL all-reduce of gradients" if world > 1 else ""),
+                                   "step = render()+L1+backward to raw leaves (L1 = each stack's own l1_loss)" + (" + 1 NCCL all-reduce of gradients" if world > 1 else ""),
                        "gaussians": P, "resolution": [W, H], "views_per_step": world, "parallelism": f"view-parallel x{world}",
                        "l2_policy": "inputs larger than L2 (>=0.7 GB of parameters streamed per step)",
                        "grad_exchange": ("none" if world == 1 else "DISABLED (diagnostic run, not a valid measurement)" if args.no_exchange else ("all-reduce 44 B/Gaussian + all-gather dRGB 12 B/Gaussian/rank, SH gradient rebuilt locally"

@@ -171,6 +171,8 @@ int lgr_multimem_allreduce(float* multicast_ptr, int rank, int world, size_t n_f
 size_t lgr_image_loss_workspace_bytes(int C, int H, int W);
 int lgr_image_loss_forward(const float* img, const float* target, int C, int H, int W, float* out2, float* dmaps, void* workspace,
                            void* cuda_stream);
+/* L1 only: out2[0] = mean|img - target|, out2[1] = 0 (no SSIM filtering); same workspace; backward = lgr_image_loss_backward with g_ssim = 0 */
+int lgr_image_l1_forward(const float* img, const float* target, int C, int H, int W, float* out2, void* workspace, void* cuda_stream);
 int lgr_image_loss_backward(const float* img, const float* target, const float* dmaps, int C, int H, int W, float g_l1, float g_ssim,
                             const float* grad_scale, float* d_img, void* cuda_stream);
 

@@ -97,6 +97,8 @@ def load():
         lib.lgr_image_loss_workspace_bytes.argtypes = [i32, i32, i32]
         lib.lgr_image_loss_forward.restype = i32
         lib.lgr_image_loss_forward.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp]
+        lib.lgr_image_l1_forward.restype = i32
+        lib.lgr_image_l1_forward.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp]
         lib.lgr_image_loss_backward.restype = i32
         lib.lgr_image_loss_backward.argtypes = [vp, vp, vp, i32, i32, i32, C.c_float, C.c_float, vp, vp, vp]
         lib.lgr_adamw_step.restype = i32

@@ -108,6 +108,31 @@ image_loss_forward_kernel(const float* __restrict__ x, const float* __restrict__
     }
 }
 
+// L1 only (utils/loss_utils.py:18-19): per-block partial sums of |x-y| over a grid-stride range, same finishing kernel
+__global__ void __launch_bounds__(256) image_l1_forward_kernel(const float* __restrict__ x, const float* __restrict__ y, long long n,
+                                                               float2* __restrict__ partial)
+{
+    __shared__ float red[8];
+    float s = 0.f;
+    const long long n4 = n >> 2;
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    const float4* y4 = reinterpret_cast<const float4*>(y);
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
+        const float4 a = x4[i], b = y4[i];
+        s += (fabsf(a.x - b.x) + fabsf(a.y - b.y)) + (fabsf(a.z - b.z) + fabsf(a.w - b.w));
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (int)(n & 3)) s += fabsf(x[(n4 << 2) + threadIdx.x] - y[(n4 << 2) + threadIdx.x]);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float a = 0.f;
+        for (int k = 0; k < 8; k++) a += red[k];
+        partial[blockIdx.x] = make_float2(a, 0.f);
+    }
+}
+
 // out[0] = mean|x-y|, out[1] = mean SSIM; fixed summation order (double accumulation in one block)
 __global__ void __launch_bounds__(256) image_loss_finish_kernel(const float2* __restrict__ partial, int n, double inv_count, float* __restrict__ out)
 {

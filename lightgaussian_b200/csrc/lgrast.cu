@@ -1463,6 +1463,27 @@ int lgr_image_loss_forward(const float* img, const float* target, int C, int H, 
     return LGR_OK;
 }
 
+int lgr_image_l1_forward(const float* img, const float* target, int C, int H, int W, float* out2, void* workspace, void* cuda_stream)
+{
+    if (!img || !target || !out2 || !workspace || C <= 0 || H <= 0 || W <= 0 || ((uintptr_t)workspace & 7) || (((uintptr_t)img | (uintptr_t)target) & 15)) {
+        g_last_error = "lgr_image_l1_forward: bad argument (images must be 16-byte aligned)";
+        return LGR_ERR_INVALID_ARG;
+    }
+    cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+    const long long n = (long long)C * H * W;
+    // never more blocks than the workspace of lgr_image_loss_workspace_bytes(C,H,W) holds partials for
+    const long long cap = (long long)((W + LT - 1) / LT) * ((H + LT - 1) / LT) * C;
+    const int blocks = (int)std::max(1LL, std::min({cap, (n / 4 + 255) / 256, 148LL * 8}));
+    {
+        ProfScope ps(ST_LOSS_FWD, stream);
+        image_l1_forward_kernel<<<blocks, 256, 0, stream>>>(img, target, n, (float2*)workspace);
+        image_loss_finish_kernel<<<1, 256, 0, stream>>>((const float2*)workspace, blocks, 1.0 / (double)n, out2);
+    }
+    LGR_LAUNCH_CHECK("image_l1_forward_kernel", false, stream);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return LGR_OK;
+}
+
 int lgr_image_loss_backward(const float* img, const float* target, const float* dmaps, int C, int H, int W, float g_l1, float g_ssim,
                             const float* grad_scale, float* d_img, void* cuda_stream)
 {

@@ -19,11 +19,18 @@ def _check(img, gt):
         raise RuntimeError(f"fused image loss expects two [C,H,W] images of the same shape, got {tuple(img.shape)} and {tuple(gt.shape)}")
 
 
-def _forward(img, gt, want_maps):
+def _forward(img, gt, want_maps, l1_only=False):
     lib = capi.load()
     C_, H, W = img.shape
     out = torch.empty(2, dtype=torch.float32, device=img.device)
     ws = torch.empty(int(lib.lgr_image_loss_workspace_bytes(C_, H, W)), dtype=torch.uint8, device=img.device)
+    if l1_only:
+        if (img.data_ptr() | gt.data_ptr()) & 15:                    # offset views: the vectorised kernel wants 16-byte alignment
+            img, gt = img.clone(), gt.clone()
+        with torch.cuda.device(img.device):
+            st = lib.lgr_image_l1_forward(img.data_ptr(), gt.data_ptr(), C_, H, W, out.data_ptr(), ws.data_ptr(), capi.current_stream_ptr(img.device))
+        capi.check(st, "lgr_image_l1_forward")
+        return out, None
     dmaps = torch.empty((3, C_, H, W), dtype=torch.float32, device=img.device) if want_maps else None
     with torch.cuda.device(img.device):
         st = lib.lgr_image_loss_forward(img.data_ptr(), gt.data_ptr(), C_, H, W, out.data_ptr(), capi.ptr(dmaps), ws.data_ptr(),
@@ -39,7 +46,7 @@ class _ImageLoss(torch.autograd.Function):
     def forward(ctx, img, gt, c_l1, c_ssim, c0):
         img_c, gt_c = img.contiguous(), gt.contiguous()
         need = ctx.needs_input_grad[0] and c_ssim != 0.0
-        out, dmaps = _forward(img_c, gt_c, need)
+        out, dmaps = _forward(img_c, gt_c, need, l1_only=(c_ssim == 0.0))
         ctx.save_for_backward(img_c, gt_c, dmaps if dmaps is not None else torch.empty(0, device=img.device))
         ctx.coef = (float(c_l1), float(c_ssim))
         return c_l1 * out[0] + c_ssim * out[1] + c0

@@ -119,6 +119,19 @@ def test_dropin_loss_utils_accepts_metrics_py_batches():
             del sys.modules[m]
 
 
+def test_l1_only_path_on_offset_views_and_odd_sizes():
+    for shape in [(3, 7, 5), (1, 1, 3), (3, 33, 17)]:
+        xn, yn = _pair(*shape, seed=9)
+        big = torch.zeros(xn.size + 1).cuda()
+        big[1:] = torch.from_numpy(xn).reshape(-1).cuda()
+        x = big[1:].reshape(shape).requires_grad_(True)              # data_ptr is 4 bytes past a 16-byte boundary
+        y = torch.from_numpy(yn).cuda()
+        out = fused.l1_loss(x, y)
+        assert abs(float(out.detach()) - float(np.abs(xn.astype(np.float64) - yn).mean())) < 1e-6
+        out.backward()
+        np.testing.assert_allclose(x.grad.cpu().numpy(), np.sign(xn - yn) / xn.size, rtol=1e-6, atol=0)
+
+
 def test_cpu_tensors_are_refused():
     with pytest.raises(RuntimeError):
         fused.l1_loss(torch.zeros(3, 4, 4), torch.zeros(3, 4, 4))
