@@ -24,8 +24,7 @@
 namespace {
 
 constexpr int VQ_TC = 64;        // codes per shared-memory tile
-constexpr int VQ_THREADS = 128;  // threads per block, 2 rows each
-constexpr int VQ_ROWS = 2 * VQ_THREADS;
+constexpr int VQ_THREADS = 128;  // threads per block, RX sample rows each
 
 __device__ __forceinline__ unsigned vq_order_bits(float f)
 {
@@ -39,24 +38,27 @@ __global__ void vq_init_best_kernel(int n, unsigned long long* __restrict__ best
     if (i < n) best[i] = ~0ull;
 }
 
-// DP = d padded to a multiple of 4 (28 for d = 27, 48 for d = 48, ...)
-template <int DP>
+// DP = d padded to a multiple of 4 (28 for d = 27, 48 for d = 48, ...); RX = sample rows held in registers per thread
+template <int DP, int RX>
 __global__ void __launch_bounds__(VQ_THREADS)
 vq_assign_kernel(int n, int d, int K, const float* __restrict__ x, const float* __restrict__ embed, int codes_per_split,
                  unsigned long long* __restrict__ best)
 {
     __shared__ __align__(16) float s_e[VQ_TC][DP];
     __shared__ float s_n[VQ_TC];
-    const int r0 = blockIdx.x * VQ_ROWS + threadIdx.x, r1 = r0 + VQ_THREADS;
-    float xa[DP], xb[DP];
+    const int row0 = blockIdx.x * (RX * VQ_THREADS) + threadIdx.x;
+    float xr[RX][DP];
 #pragma unroll
-    for (int j = 0; j < DP; j++) {
-        xa[j] = (j < d && r0 < n) ? -2.0f * x[(size_t)r0 * d + j] : 0.f;
-        xb[j] = (j < d && r1 < n) ? -2.0f * x[(size_t)r1 * d + j] : 0.f;
+    for (int r = 0; r < RX; r++) {
+        const int row = row0 + r * VQ_THREADS;
+#pragma unroll
+        for (int j = 0; j < DP; j++) xr[r][j] = (j < d && row < n) ? -2.0f * x[(size_t)row * d + j] : 0.f;
     }
     const int c_begin = blockIdx.y * codes_per_split, c_end = min(K, c_begin + codes_per_split);
-    float best_a = 3.0e38f, best_b = 3.0e38f;
-    int arg_a = c_begin, arg_b = c_begin;
+    float bestv[RX];
+    int arg[RX];
+#pragma unroll
+    for (int r = 0; r < RX; r++) { bestv[r] = 3.0e38f; arg[r] = c_begin; }
     for (int c0 = c_begin; c0 < c_end; c0 += VQ_TC) {
         __syncthreads();
         for (int t = threadIdx.x; t < VQ_TC * DP; t += VQ_THREADS) {
@@ -73,35 +75,47 @@ vq_assign_kernel(int n, int d, int K, const float* __restrict__ x, const float* 
         __syncthreads();
 #pragma unroll 2
         for (int c = 0; c < VQ_TC; c++) {
-            float da = s_n[c], db = da;
+            float dist[RX];
+            const float nrm = s_n[c];
+#pragma unroll
+            for (int r = 0; r < RX; r++) dist[r] = nrm;
             const float4* e4 = reinterpret_cast<const float4*>(s_e[c]);
 #pragma unroll
             for (int q = 0; q < DP / 4; q++) {
                 const float4 e = e4[q];
-                da = fmaf(xa[4 * q + 0], e.x, da); db = fmaf(xb[4 * q + 0], e.x, db);
-                da = fmaf(xa[4 * q + 1], e.y, da); db = fmaf(xb[4 * q + 1], e.y, db);
-                da = fmaf(xa[4 * q + 2], e.z, da); db = fmaf(xb[4 * q + 2], e.z, db);
-                da = fmaf(xa[4 * q + 3], e.w, da); db = fmaf(xb[4 * q + 3], e.w, db);
+#pragma unroll
+                for (int r = 0; r < RX; r++) {
+                    dist[r] = fmaf(xr[r][4 * q + 0], e.x, dist[r]);
+                    dist[r] = fmaf(xr[r][4 * q + 1], e.y, dist[r]);
+                    dist[r] = fmaf(xr[r][4 * q + 2], e.z, dist[r]);
+                    dist[r] = fmaf(xr[r][4 * q + 3], e.w, dist[r]);
+                }
             }
-            if (da < best_a) { best_a = da; arg_a = c0 + c; }
-            if (db < best_b) { best_b = db; arg_b = c0 + c; }
+#pragma unroll
+            for (int r = 0; r < RX; r++)
+                if (dist[r] < bestv[r]) { bestv[r] = dist[r]; arg[r] = c0 + c; }
         }
     }
-    if (r0 < n) atomicMin(&best[r0], ((unsigned long long)vq_order_bits(best_a) << 32) | (unsigned)arg_a);
-    if (r1 < n) atomicMin(&best[r1], ((unsigned long long)vq_order_bits(best_b) << 32) | (unsigned)arg_b);
+#pragma unroll
+    for (int r = 0; r < RX; r++) {
+        const int row = row0 + r * VQ_THREADS;
+        if (row < n) atomicMin(&best[row], ((unsigned long long)vq_order_bits(bestv[r]) << 32) | (unsigned)arg[r]);
+    }
 }
 
 template <int DP>
 void vq_launch_assign(int n, int d, int K, const float* x, const float* embed, unsigned long long* best, cudaStream_t stream)
 {
-    const int row_tiles = (n + VQ_ROWS - 1) / VQ_ROWS;
+    constexpr int RX = DP <= 32 ? 4 : 2;                           // 4 rows x 28 values still fit the register file without spills
+    const int rows = RX * VQ_THREADS;
+    const int row_tiles = (n + rows - 1) / rows;
     const int code_tiles = (K + VQ_TC - 1) / VQ_TC;
-    int splits = (4 * 148 * 5 + row_tiles - 1) / row_tiles;        // aim at >= 4 waves of 148 SMs x 5 resident blocks
+    int splits = (4 * 148 * 3 + row_tiles - 1) / row_tiles;        // aim at >= 4 waves of 148 SMs x 3 resident blocks
     splits = max(1, min(splits, code_tiles));
     const int tiles_per_split = (code_tiles + splits - 1) / splits;
     const int codes_per_split = tiles_per_split * VQ_TC;
     splits = (K + codes_per_split - 1) / codes_per_split;
-    vq_assign_kernel<DP><<<dim3(row_tiles, splits), VQ_THREADS, 0, stream>>>(n, d, K, x, embed, codes_per_split, best);
+    vq_assign_kernel<DP, RX><<<dim3(row_tiles, splits), VQ_THREADS, 0, stream>>>(n, d, K, x, embed, codes_per_split, best);
 }
 
 // idx[i] = low word of best[i]; optional weighted accumulation for the EMA step.  weight == nullptr: unit weights; otherwise the
