@@ -35,6 +35,12 @@ def mean_psnr(pc, cams, targets, pipe, bg):
 
 def test_prune_finetune_vq_pipeline(tmp_path):
     scene = make_scene(8000, sh_degree=3, seed=51, scale_mult=1.6)
+    # real scenes have structured SH (that is what a codebook exploits): draw the colours from a palette of 96 SH vectors + noise
+    rng = np.random.default_rng(7)
+    palette = np.concatenate([rng.standard_normal((96, 1, 3)), 0.2 * rng.standard_normal((96, 15, 3))], axis=1).astype(np.float32)
+    pick = rng.integers(0, 96, 8000)
+    sh = palette[pick] + 0.01 * rng.standard_normal((8000, 16, 3)).astype(np.float32)
+    scene["raw"]["features_dc"], scene["raw"]["features_rest"] = np.ascontiguousarray(sh[:, :1]), np.ascontiguousarray(sh[:, 1:])
     pc = GaussianParams(scene["raw"], 3, "cuda")
     for _, attr, _ in NAMES:                                   # nn.Parameters, as GaussianModel holds them
         setattr(pc, attr, torch.nn.Parameter(getattr(pc, attr).detach()))
@@ -107,5 +113,6 @@ def test_prune_finetune_vq_pipeline(tmp_path):
     zr[~kept] = 0
     zero._features_rest = zr
     p_zero = mean_psnr(zero, cams, targets, pipe, bg)
+    print(f"PSNR pruned {p_pruned:.2f} tuned {p_tuned:.2f} vq {p_vq:.2f} (SH of the vq'd 60 % zeroed instead: {p_zero:.2f})")
     assert p_vq > p_tuned - 3.0, (p_tuned, p_vq)
-    assert p_vq >= p_zero - 0.05, (p_vq, p_zero)
+    assert p_vq > p_zero + 1.0, (p_vq, p_zero)
