@@ -142,6 +142,10 @@ int lgr_backward_raw_begin(const lgr_view* view, int P, int num_rendered, const 
                            char* image_blob, const float* dL_dout_color, float* d_rgb, void* cuda_stream);
 int lgr_backward_raw_end(const lgr_view* view, int P, int M, const lgr_raw_params* params, const int32_t* radii, char* geometry_blob,
                          const lgr_raw_grads* grads, float* dL_dmeans2D, void* cuda_stream);
+/* stage 2 for Gaussians [first, first+count) only (first a multiple of 256): lets a view-parallel caller exchange one range's
+ * gradients while the next range is computed */
+int lgr_backward_raw_end_range(const lgr_view* v, int P, int M, const lgr_raw_params* params, const int32_t* radii, char* geometry_blob,
+                               const lgr_raw_grads* grads, float* dL_dmeans2D, int first, int count, void* cuda_stream);
 
 /* View-parallel training: for one view dL/dSH[k][c] = basis_k(dir) * dRGB[c] is rank-1 per Gaussian
  * (RAST/cuda_rasterizer/backward.cu:44-97), so ranks exchange dRGB (12 B/Gaussian/view, all-gather) instead of the

@@ -91,6 +91,8 @@ def load():
         lib.lgr_backward_raw_begin.argtypes = [C.POINTER(LgrView), i32, i32, vp, vp, vp, vp, vp, vp, vp]
         lib.lgr_backward_raw_end.restype = i32
         lib.lgr_backward_raw_end.argtypes = [C.POINTER(LgrView), i32, i32, C.POINTER(LgrRawParams), vp, vp, C.POINTER(LgrRawGrads), vp, vp]
+        lib.lgr_backward_raw_end_range.restype = i32
+        lib.lgr_backward_raw_end_range.argtypes = [C.POINTER(LgrView), i32, i32, C.POINTER(LgrRawParams), vp, vp, C.POINTER(LgrRawGrads), vp, i32, i32, vp]
         lib.lgr_peer_allreduce.restype = i32
         lib.lgr_peer_allreduce.argtypes = [C.POINTER(C.c_void_p), i32, i32, C.c_size_t, vp]
         lib.lgr_image_loss_workspace_bytes.restype = C.c_size_t

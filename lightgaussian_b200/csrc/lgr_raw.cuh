@@ -219,6 +219,7 @@ struct RawBackArgs {
     float* d_rotation;
     float* d_opacity;
     float* dL_dmeans2D;
+    int block0;    // first 256-Gaussian block this launch covers (ranged launches of the view-parallel exchange)
     float* d_rgb;  // optional [P,3]: clamp-masked dL/dRGB (compact SH gradient factor); when set and d_rest == NULL the dense SH rows are not written
 };
 
@@ -243,7 +244,7 @@ __global__ void __launch_bounds__(256) preprocess_backward_raw_kernel(RawBackArg
     const float* proj = s_cam + 16;
     const float* cam = s_cam + 32;
 
-    const int first = blockIdx.x * 256 + warp * 32;
+    const int first = (a.block0 + (int)blockIdx.x) * 256 + warp * 32;
     if (first >= a.P) return;
     const int n = min(32, a.P - first);
     const int i = first + lane;

@@ -1315,8 +1315,20 @@ int lgr_backward_raw_begin(const lgr_view* v, int P, int num_rendered, const int
 int lgr_backward_raw_end(const lgr_view* v, int P, int M, const lgr_raw_params* params, const int32_t* radii, char* geometry_blob,
                          const lgr_raw_grads* grads, float* dL_dmeans2D, void* cuda_stream)
 {
+    return lgr_backward_raw_end_range(v, P, M, params, radii, geometry_blob, grads, dL_dmeans2D, 0, P, cuda_stream);
+}
+
+// the same for Gaussians [first, first+count) only; first must be a multiple of 256.  Lets the caller start exchanging the gradients
+// of one range while the next range is still being computed.
+int lgr_backward_raw_end_range(const lgr_view* v, int P, int M, const lgr_raw_params* params, const int32_t* radii, char* geometry_blob,
+                               const lgr_raw_grads* grads, float* dL_dmeans2D, int first, int count, void* cuda_stream)
+{
     cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
-    if (P == 0) return LGR_OK;
+    if (P == 0 || count == 0) return LGR_OK;
+    if (first < 0 || count < 0 || (first & 255) || first + (long long)count > P) {
+        g_last_error = "lgr_backward_raw_end_range: the range must start at a multiple of 256 and lie inside [0, P)";
+        return LGR_ERR_INVALID_ARG;
+    }
     const bool compact = grads && grads->features_rest == nullptr;
     if (!v || P < 0 || M < 1 || !params || !grads || !radii || !geometry_blob || !dL_dmeans2D || !grads->xyz ||
         (!compact && (!grads->features_dc || (M > 1 && !grads->features_rest))) || !grads->scaling || !grads->rotation || !grads->opacity) {
@@ -1343,12 +1355,14 @@ int lgr_backward_raw_end(const lgr_view* v, int P, int M, const lgr_raw_params* 
     a.d_xyz = grads->xyz; a.d_dc = grads->features_dc; a.d_rest = grads->features_rest; a.d_scaling = grads->scaling;
     a.d_rotation = grads->rotation; a.d_opacity = grads->opacity; a.dL_dmeans2D = dL_dmeans2D;
     a.d_rgb = grads->rgb;
+    a.block0 = first / 256;
+    a.P = first + count;                       // the kernel's bound check: blocks of this launch never run past the range
     if (compact) { a.d_rest = nullptr; a.d_dc = nullptr; }
     const size_t smem = raw_smem_bytes(M);
     LGR_CUDA_TRY(cudaFuncSetAttribute(preprocess_backward_raw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     {
         ProfScope ps(ST_PREPROCESS_BWD, stream);
-        preprocess_backward_raw_kernel<<<(P + 255) / 256, 256, smem, stream>>>(a);
+        preprocess_backward_raw_kernel<<<(count + 255) / 256, 256, smem, stream>>>(a);
     }
     LGR_LAUNCH_CHECK("preprocess_backward_raw_kernel", debug, stream);
     return LGR_OK;

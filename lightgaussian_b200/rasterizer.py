@@ -435,11 +435,26 @@ def _symm_exchange(device, P, world, group):
     return _symm_cache[key]
 
 
+def _exchange_chunks(P):
+    """[(first, count)] ranges of Gaussians, boundaries at multiples of 256 (LGR_EXCHANGE_CHUNKS ranges, default 4; 1 = one all-reduce)"""
+    import os
+    n = max(1, int(os.environ.get("LGR_EXCHANGE_CHUNKS", "4")))
+    blocks = (P + 255) // 256
+    n = min(n, blocks)
+    out, b0 = [], 0
+    for c in range(n):
+        b1 = blocks * (c + 1) // n
+        if b1 > b0:
+            out.append((b0 * 256, min(P, b1 * 256) - b0 * 256))
+        b0 = b1
+    return out
+
+
 def _backward_raw_exchange(rs, num_rendered, grad_out_color, xyz, dc, rest, scaling, rotation, opacity, radii, geom, binning, img, world, grp):
     """The view-parallel backward: every collective is issued as early as its input exists so that it overlaps kernels.
 
-        main stream :  blend backward + dRGB extract | K7+K8 (small leaves -> flat)            | wait
-        NCCL stream :                                | all-gather dRGB, campos | all-reduce flat |
+        main stream :  blend backward + dRGB extract | K7+K8 range 0 | range 1 | range 2 | range 3     | wait
+        NCCL stream :                                | all-gather dRGB, campos | all-reduce r0 | r1 | r2 | r3 |
         side stream :                                                          | rebuild SH gradient from all views |
     """
     import torch.distributed as dist
@@ -475,9 +490,22 @@ def _backward_raw_exchange(rs, num_rendered, grad_out_color, xyz, dc, rest, scal
         w_cam = dist.all_gather_into_tensor(all_cam, keep[3].reshape(1, 3), group=grp, async_op=True)
         params = _raw_struct(xyz, dc, rest, scaling, rotation, opacity)
         grads = _raw_grads_struct(g_xyz, None, None, g_scal, g_rot, g_op, rgb=None)
-        st = lib.lgr_backward_raw_end(C.byref(view), P, M, C.byref(params), radii.data_ptr(), geom.data_ptr(), C.byref(grads),
-                                      g2d.data_ptr(), main.cuda_stream)
-        capi.check(st, "lgr_backward_raw_end")
+        # K7+K8 in ranges of Gaussians: the all-reduce of one range's small-leaf gradients (four slices of the flat buffer, coalesced
+        # into one NCCL launch) runs while the next range is still being computed
+        chunks = _exchange_chunks(P) if xb is None else [(0, P)]
+        w_flat = []
+        for (c0, cn) in chunks:
+            st = lib.lgr_backward_raw_end_range(C.byref(view), P, M, C.byref(params), radii.data_ptr(), geom.data_ptr(), C.byref(grads),
+                                                g2d.data_ptr(), c0, cn, main.cuda_stream)
+            capi.check(st, "lgr_backward_raw_end_range")
+            if xb is None:
+                if len(chunks) == 1:
+                    w_flat.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=grp, async_op=True))
+                else:
+                    with dist.distributed_c10d._coalescing_manager(group=grp, device=device, async_ops=True) as cm:
+                        for t in (g_rot, g_xyz, g_scal, g_op):
+                            dist.all_reduce(t[c0:c0 + cn], op=dist.ReduceOp.SUM, group=grp)
+                    w_flat.append(cm)
         if ev:
             ev[2].record(main)
         # critical path first: the small-leaf reduction runs on a HIGH-priority stream so that its blocks are scheduled ahead
@@ -487,9 +515,6 @@ def _backward_raw_exchange(rs, num_rendered, grad_out_color, xyz, dc, rest, scal
             hp.wait_stream(main)
             with torch.cuda.stream(hp):
                 xb.all_reduce_(flat_full, hp)  # our peer-memory reduction over NVLink
-            w_flat = None
-        else:
-            w_flat = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=grp, async_op=True)
         with torch.cuda.stream(side):                                                            # overlaps the all-reduce
             w_rgb.wait()
             w_cam.wait()
@@ -499,7 +524,8 @@ def _backward_raw_exchange(rs, num_rendered, grad_out_color, xyz, dc, rest, scal
         if xb is not None:
             main.wait_stream(hp)
         else:
-            w_flat.wait()
+            for w in w_flat:
+                w.wait()
         main.wait_stream(side)
         if ev:
             ev[3].record(main)
