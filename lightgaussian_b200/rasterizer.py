@@ -436,9 +436,11 @@ def _symm_exchange(device, P, world, group):
 
 
 def _exchange_chunks(P):
-    """[(first, count)] ranges of Gaussians, boundaries at multiples of 256 (LGR_EXCHANGE_CHUNKS ranges, default 4; 1 = one all-reduce)"""
+    """[(first, count)] ranges of Gaussians, boundaries at multiples of 256.  LGR_EXCHANGE_CHUNKS ranges; default 1 = one all-reduce
+    after the whole K7+K8: measured on 2 B200s, 2 / 4 ranges were SLOWER (624 / 581 vs 672 views/s): the NCCL kernels of the earlier ranges
+    take SMs and HBM bandwidth from the ranges still being computed (K7+K8 0.20 -> 0.38 ms) and the link was not idle to begin with."""
     import os
-    n = max(1, int(os.environ.get("LGR_EXCHANGE_CHUNKS", "4")))
+    n = max(1, int(os.environ.get("LGR_EXCHANGE_CHUNKS", "1")))
     blocks = (P + 255) // 256
     n = min(n, blocks)
     out, b0 = [], 0
@@ -453,8 +455,8 @@ def _exchange_chunks(P):
 def _backward_raw_exchange(rs, num_rendered, grad_out_color, xyz, dc, rest, scaling, rotation, opacity, radii, geom, binning, img, world, grp):
     """The view-parallel backward: every collective is issued as early as its input exists so that it overlaps kernels.
 
-        main stream :  blend backward + dRGB extract | K7+K8 range 0 | range 1 | range 2 | range 3     | wait
-        NCCL stream :                                | all-gather dRGB, campos | all-reduce r0 | r1 | r2 | r3 |
+        main stream :  blend backward + dRGB extract | K7+K8 (small leaves -> flat)            | wait
+        NCCL stream :                                | all-gather dRGB, campos | all-reduce flat |
         side stream :                                                          | rebuild SH gradient from all views |
     """
     import torch.distributed as dist
@@ -490,8 +492,8 @@ def _backward_raw_exchange(rs, num_rendered, grad_out_color, xyz, dc, rest, scal
         w_cam = dist.all_gather_into_tensor(all_cam, keep[3].reshape(1, 3), group=grp, async_op=True)
         params = _raw_struct(xyz, dc, rest, scaling, rotation, opacity)
         grads = _raw_grads_struct(g_xyz, None, None, g_scal, g_rot, g_op, rgb=None)
-        # K7+K8 in ranges of Gaussians: the all-reduce of one range's small-leaf gradients (four slices of the flat buffer, coalesced
-        # into one NCCL launch) runs while the next range is still being computed
+        # optional (LGR_EXCHANGE_CHUNKS > 1, measured slower, see _exchange_chunks): K7+K8 in ranges of Gaussians, the all-reduce of one
+        # range's small-leaf gradients (four slices of the flat buffer, coalesced into one NCCL launch) overlapping the next range
         chunks = _exchange_chunks(P) if xb is None else [(0, P)]
         w_flat = []
         for (c0, cn) in chunks:
