@@ -54,6 +54,11 @@ assert g.rotation_activation is torch.nn.functional.normalize
 from arguments import PipelineParams
 from lightgaussian_b200 import optim
 assert GM.prune_points is optim.prune_points and GM.training_setup.__wrapped__ is not None     # row N3 installed by the drop-in
+import vectree.utils, vectree.vq, lightgaussian_b200.vectree                                    # row N4 overlay
+assert vectree.utils.load_vqgaussian is lightgaussian_b200.vectree.load_vqgaussian
+assert vectree.utils.write_ply_data.__code__.co_filename.startswith("/root/reference/") and vectree.vq.__file__.startswith("/root/reference/")
+import scene.gaussian_model as sgm
+assert sgm.load_vqgaussian is lightgaussian_b200.vectree.load_vqgaussian                       # what GaussianModel.load_vq calls (:420-422)
 print("ok")
 """ % (os.path.join(ROOT, "dropin"), os.path.join(ROOT, "dropin"))
     env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(ROOT, "dropin"), ROOT, REF]))
