@@ -600,6 +600,16 @@ def main():
 
     if args.impl == "ours" and os.environ.get("LGR_EXCHANGE_TIMING", "0") == "1":
         print(f"[rank {rank}] exchange timing: {rasterizer.exchange_timing_report()}", file=sys.stderr)
+    xdesc, xbytes = None, None
+    if fused_exchange:
+        mode, rows = rasterizer.exchange_info(world)
+        if mode == "sparse-p2p":
+            xdesc = (f"sparse over NVLink peer memory: each rank publishes bitmap + 64-byte rows of the Gaussians with a non-zero gradient "
+                     f"({rows} of {P} in rank 0's last view) and reads every peer's rows in its accumulate kernel; no NCCL call")
+            xbytes = (world - 1) * (rows * 64 + P // 4)
+        else:
+            xdesc = "dense (NCCL): all-reduce 44 B/Gaussian + all-gather dRGB 12 B/Gaussian/rank, SH gradient rebuilt locally"
+            xbytes = P * 44 + P * 12 * world
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -609,9 +619,9 @@ def main():
                                    "step = render()+L1+backward to raw leaves (L1 = each stack's own l1_loss)" + (" + 1 NCCL all-reduce of gradients" if world > 1 else ""),
                        "gaussians": P, "resolution": [W, H], "views_per_step": world, "parallelism": f"view-parallel x{world}",
                        "l2_policy": "inputs larger than L2 (>=0.7 GB of parameters streamed per step)",
-                       "grad_exchange": ("none" if world == 1 else "DISABLED (diagnostic run, not a valid measurement)" if args.no_exchange else ("all-reduce 44 B/Gaussian + all-gather dRGB 12 B/Gaussian/rank, SH gradient rebuilt locally"
-                                                                    if fused_exchange else "dense all-reduce")),
-                       "grad_exchange_bytes_per_rank": 0 if world == 1 else (P * 44 + P * 12 * world if fused_exchange else grad_bytes),
+                       "grad_exchange": ("none" if world == 1 else "DISABLED (diagnostic run, not a valid measurement)" if args.no_exchange else
+                                         (xdesc if fused_exchange else "dense all-reduce")),
+                       "grad_exchange_bytes_per_rank": 0 if world == 1 else (xbytes if fused_exchange else grad_bytes),
                        "fused_activations": bool(args.impl == "ours" and os.environ.get("LGR_FUSED", "1") != "0")},
             "clocks": clocks, "gpu_launches": launches,
         }

@@ -180,6 +180,20 @@ int lgr_image_l1_forward(const float* img, const float* target, int C, int H, in
 int lgr_image_loss_backward(const float* img, const float* target, const float* dmaps, int C, int H, int W, float g_l1, float g_ssim,
                             const float* grad_scale, float* d_img, void* cuda_stream);
 
+/* ---- sparse view-parallel gradient exchange over peer memory ----
+ * Only ~13 % of the Gaussians get a non-zero gradient from one view.  lgr_backward_raw_sparse_pack (after lgr_backward_raw_begin) runs the
+ * per-Gaussian backward on those only and publishes, in `exchange_buffer` (lgr_sparse_exchange_bytes(P) bytes, 256-byte aligned, mapped into
+ * every peer): the view's camera position, a bitmap + prefix counts of the non-zero Gaussians and their 64-byte gradient rows.  After a
+ * cross-GPU barrier, lgr_backward_raw_sparse_accumulate reads the rows of all `world` buffers (peer_buffers[r] = rank r's buffer as mapped
+ * here; P2P loads) in rank order and writes the six dense leaf gradients, summed over the views, bit-identically on every rank.
+ * workspace: lgr_sparse_workspace_bytes(P) bytes of local scratch.  dL_dmeans2D (local view only) is written dense. */
+size_t lgr_sparse_exchange_bytes(int P);
+size_t lgr_sparse_workspace_bytes(int P);
+int lgr_backward_raw_sparse_pack(const lgr_view* v, int P, int M, const lgr_raw_params* params, const int32_t* radii, char* geometry_blob,
+                                 void* exchange_buffer, void* workspace, float* dL_dmeans2D, void* cuda_stream);
+int lgr_backward_raw_sparse_accumulate(int P, int M, int sh_degree, int world, const void* const* peer_buffers, const float* xyz,
+                                       const lgr_raw_grads* grads, void* cuda_stream);
+
 /* ---- optimizer side of the training loops ----
  * lgr_adamw_step: torch.optim.AdamW's default (foreach) update, amsgrad off, for up to 8 tensors in ONE launch; replaces
  * `gaussians.optimizer.step()` (prune_finetune.py:287, optimizer built at scene/gaussian_model.py:184-217).  `step` is the

@@ -111,6 +111,14 @@ def load():
         lib.lgr_compact_plan.argtypes = [i32, vp, vp, vp, C.c_size_t, C.POINTER(C.c_int32), vp]
         lib.lgr_compact_rows.restype = i32
         lib.lgr_compact_rows.argtypes = [i32, vp, i32, C.POINTER(LgrCompactTensor), vp]
+        lib.lgr_sparse_exchange_bytes.restype = C.c_size_t
+        lib.lgr_sparse_exchange_bytes.argtypes = [i32]
+        lib.lgr_sparse_workspace_bytes.restype = C.c_size_t
+        lib.lgr_sparse_workspace_bytes.argtypes = [i32]
+        lib.lgr_backward_raw_sparse_pack.restype = i32
+        lib.lgr_backward_raw_sparse_pack.argtypes = [C.POINTER(LgrView), i32, i32, C.POINTER(LgrRawParams), vp, vp, vp, vp, vp, vp]
+        lib.lgr_backward_raw_sparse_accumulate.restype = i32
+        lib.lgr_backward_raw_sparse_accumulate.argtypes = [i32, i32, i32, i32, C.POINTER(C.c_void_p), vp, C.POINTER(LgrRawGrads), vp]
         lib.lgr_vq_workspace_bytes.restype = C.c_size_t
         lib.lgr_vq_workspace_bytes.argtypes = [C.c_int64]
         lib.lgr_vq_assign.restype = i32

@@ -47,12 +47,13 @@ std::atomic<uint64_t> g_launches{0};
 
 // ---- optional per-stage device timing (CUDA events on the launch stream), used by bench.py's roofline ----
 enum StageId { ST_PREPROCESS = 0, ST_DEPTH_SORT, ST_SCAN, ST_EMIT, ST_TILE_SORT, ST_RANGES, ST_BLEND_FWD, ST_BLEND_FWD_COUNT,
-               ST_SCORE, ST_BLEND_BWD, ST_PREPROCESS_BWD, ST_MEMSET, ST_SH_GRAD, ST_PEER_ALLREDUCE, ST_LOSS_FWD, ST_LOSS_BWD, ST_ADAMW, ST_COMPACT, ST_VQ_ASSIGN, ST_VQ_UPDATE, ST_COUNT };
+               ST_SCORE, ST_BLEND_BWD, ST_PREPROCESS_BWD, ST_MEMSET, ST_SH_GRAD, ST_PEER_ALLREDUCE, ST_LOSS_FWD, ST_LOSS_BWD, ST_ADAMW, ST_COMPACT, ST_VQ_ASSIGN, ST_VQ_UPDATE, ST_SPARSE_PACK, ST_SPARSE_ACC, ST_COUNT };
 const char* const kStageNames[ST_COUNT] = {"preprocess_kernel", "depth_sort(cub)", "scan(cub)", "emit_kernel", "tile_sort(cub)",
                                            "ranges_kernel", "blend_forward_kernel", "blend_forward_kernel<count>", "score_kernel",
                                            "blend_backward_kernel", "preprocess_backward_kernel", "memset", "sh_grad_from_views_kernel",
                                            "peer_allreduce_kernel", "image_loss_forward_kernel", "image_loss_backward_kernel", "adamw_multi_kernel",
-                                           "compact_gather_kernel", "vq_assign_kernel", "vq_ema_kernels"};
+                                           "compact_gather_kernel", "vq_assign_kernel", "vq_ema_kernels", "sparse_pack(flag+scan+index+K8)",
+                                           "sparse_accumulate_kernel"};
 struct ProfRecord { int stage; cudaEvent_t a, b; };
 bool g_prof_on = false;
 std::vector<ProfRecord> g_prof_records;
@@ -917,6 +918,7 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(PreBackArgs a)
 
 }  // namespace
 #include "lgr_raw.cuh"
+#include "lgr_sparse.cuh"
 #include "lgr_loss.cuh"
 #include "lgr_optim.cuh"
 #include "lgr_vq.cuh"
@@ -1375,6 +1377,100 @@ int lgr_backward_raw(const lgr_view* v, int P, int M, int num_rendered, const lg
     const int st = lgr_backward_raw_begin(v, P, num_rendered, radii, geometry_blob, binning_blob, image_blob, dL_dout_color, nullptr, cuda_stream);
     if (st != LGR_OK) return st;
     return lgr_backward_raw_end(v, P, M, params, radii, geometry_blob, grads, dL_dmeans2D, cuda_stream);
+}
+
+// ---- sparse view-parallel exchange (lgr_sparse.cuh) ----
+size_t lgr_sparse_exchange_bytes(int P) { return P > 0 ? sparse_layout(P).total * 4 : 256; }
+
+static size_t sparse_scan_bytes(int P)
+{
+    size_t bytes = 0;
+    cub::DeviceScan::ExclusiveSum((void*)nullptr, bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (P + 31) / 32);
+    return bytes;
+}
+
+size_t lgr_sparse_workspace_bytes(int P)
+{
+    if (P <= 0) return 256;
+    return align_up((size_t)((P + 31) / 32) * 4, 256) + align_up((size_t)P * 4, 256) + align_up(sparse_scan_bytes(P), 256) + 256;
+}
+
+int lgr_backward_raw_sparse_pack(const lgr_view* v, int P, int M, const lgr_raw_params* params, const int32_t* radii, char* geometry_blob,
+                                 void* exchange_buffer, void* workspace, float* dL_dmeans2D, void* cuda_stream)
+{
+    cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+    if (P == 0) return LGR_OK;
+    if (!v || P < 0 || M < 1 || !params || !radii || !geometry_blob || !exchange_buffer || !workspace || !dL_dmeans2D ||
+        ((uintptr_t)exchange_buffer & 255) || ((uintptr_t)workspace & 255) || ((uintptr_t)params->rotation & 15)) {
+        g_last_error = "lgr_backward_raw_sparse_pack: missing argument or misaligned buffer (exchange buffer and workspace: 256 bytes)";
+        return LGR_ERR_INVALID_ARG;
+    }
+    const bool debug = v->debug != 0;
+    const int W = v->image_width, H = v->image_height;
+    GeometryState geo = carve_geometry(geometry_blob, (size_t)P);
+    const SparseLayout L = sparse_layout(P);
+    uint32_t* xb = static_cast<uint32_t*>(exchange_buffer);
+    const int w32 = (P + 31) / 32;
+    char* ws = static_cast<char*>(workspace);
+    uint32_t* popc = reinterpret_cast<uint32_t*>(ws);
+    int* idx = reinterpret_cast<int*>(ws + align_up((size_t)w32 * 4, 256));
+    void* cub_tmp = ws + align_up((size_t)w32 * 4, 256) + align_up((size_t)P * 4, 256);
+    size_t cub_bytes = sparse_scan_bytes(P);
+    RawBackArgs a;
+    memset(&a, 0, sizeof(a));
+    a.P = P; a.D = v->sh_degree; a.M = M; a.W = W; a.H = H;
+    a.fy = H / (2.0f * v->tan_fovy);
+    a.fx = W / (2.0f * v->tan_fovx);
+    a.tanx = v->tan_fovx; a.tany = v->tan_fovy; a.mod = v->scale_modifier;
+    a.xyz = params->xyz; a.dc = params->features_dc; a.rest = params->features_rest; a.scaling = params->scaling;
+    a.rotation = params->rotation; a.cov3D = geo.cov3D; a.conic_opacity = geo.conic_opacity;
+    a.view = v->viewmatrix; a.proj = v->projmatrix; a.campos = v->campos;
+    a.radii = radii; a.clamped = geo.clamped; a.acc = geo.grad_acc;
+    a.dL_dmeans2D = dL_dmeans2D;
+    {
+        ProfScope ps(ST_SPARSE_PACK, stream);
+        LGR_CUDA_TRY(cudaMemsetAsync(dL_dmeans2D, 0, sizeof(float) * 3 * (size_t)P, stream));
+        sparse_flag_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, radii, geo.grad_acc, xb + L.bitmap, popc);
+        LGR_CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, popc, xb + L.prefix, w32, stream));
+        sparse_index_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, xb + L.bitmap, xb + L.prefix, idx, xb + L.hdr, v->campos);
+        preprocess_backward_sparse_kernel<<<(P + 255) / 256, 256, 0, stream>>>(a, idx, xb + L.hdr, reinterpret_cast<float*>(xb + L.rows));
+    }
+    LGR_LAUNCH_CHECK("preprocess_backward_sparse_kernel", debug, stream);
+    return LGR_OK;
+}
+
+int lgr_backward_raw_sparse_accumulate(int P, int M, int sh_degree, int world, const void* const* peer_buffers, const float* xyz,
+                                       const lgr_raw_grads* grads, void* cuda_stream)
+{
+    if (P == 0) return LGR_OK;
+    if (P < 0 || M < 2 || M > 16 || sh_degree < 0 || sh_degree > 3 || (sh_degree + 1) * (sh_degree + 1) > M || world < 1 || world > 8 ||
+        !peer_buffers || !xyz || !grads || !grads->xyz || !grads->features_dc || !grads->features_rest || !grads->scaling || !grads->rotation ||
+        !grads->opacity || ((uintptr_t)grads->rotation & 15) || ((uintptr_t)grads->features_rest & 15) || ((uintptr_t)grads->features_dc & 15)) {
+        g_last_error = "lgr_backward_raw_sparse_accumulate: bad argument (1..8 ranks, SH degree <= 3, 2 <= M <= 16, 16-byte aligned gradient rows)";
+        return LGR_ERR_INVALID_ARG;
+    }
+    SparseAccArgs a;
+    memset(&a, 0, sizeof(a));
+    a.P = P; a.D = sh_degree; a.M = M; a.world = world;
+    for (int r = 0; r < world; r++) {
+        if (!peer_buffers[r] || ((uintptr_t)peer_buffers[r] & 255)) {
+            g_last_error = "lgr_backward_raw_sparse_accumulate: peer buffer missing or not 256-byte aligned";
+            return LGR_ERR_INVALID_ARG;
+        }
+        a.peer[r] = static_cast<const uint32_t*>(peer_buffers[r]);
+    }
+    a.xyz = xyz;
+    a.d_xyz = grads->xyz; a.d_dc = grads->features_dc; a.d_rest = grads->features_rest; a.d_scaling = grads->scaling;
+    a.d_rotation = grads->rotation; a.d_opacity = grads->opacity;
+    cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+    const size_t smem = raw_smem_bytes(M);
+    LGR_CUDA_TRY(cudaFuncSetAttribute(sparse_accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {
+        ProfScope ps(ST_SPARSE_ACC, stream);
+        sparse_accumulate_kernel<<<(P + 255) / 256, 256, smem, stream>>>(a);
+    }
+    LGR_LAUNCH_CHECK("sparse_accumulate_kernel", false, stream);
+    return LGR_OK;
 }
 
 int lgr_peer_allreduce(float* const* peer_buffers, int rank, int world, size_t n_floats, void* cuda_stream)

@@ -16,6 +16,8 @@ from __future__ import annotations
 import ctypes as C
 from typing import NamedTuple
 
+import os as _os
+
 import torch
 import torch.nn as nn
 
@@ -335,7 +337,12 @@ class _RasterizeRawLeaves(torch.autograd.Function):
         xyz, dc, rest, scaling, rotation, opacity, radii, geom, binning, img = ctx.saved_tensors
         world = _exchange["world"]
         exchange = world > 1 and xyz.size(0) != 0 and rest.size(1) > 0
-        if not exchange:
+        sparse_single = world == 1 and _os.environ.get("LGR_SPARSE_SINGLE", "0") == "1" and xyz.size(0) != 0 and rest.size(1) > 0
+        xs = _sparse_exchange(xyz.device, xyz.size(0), world, _exchange["group"]) if (exchange or sparse_single) else None
+        if xs is not None:
+            g, g2d = _backward_raw_sparse(xs, rs, ctx.num_rendered, grad_out_color, xyz, dc, rest, scaling, rotation, opacity, radii, geom,
+                                          binning, img, world)
+        elif not exchange:
             g, g2d, _, _ = backward_raw_native(rs, ctx.num_rendered, grad_out_color, xyz, dc, rest, scaling, rotation, opacity, radii,
                                                geom, binning, img, compact=False)
         else:
@@ -433,6 +440,110 @@ def _symm_exchange(device, P, world, group):
         dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
         _symm_cache[key] = xb if int(flag.item()) == 1 else None
     return _symm_cache[key]
+
+
+class _SparseExchange:
+    """Two alternating exchange buffers per rank in NVLink symmetric memory (torch.distributed._symmetric_memory), each mapped into every
+    peer, for the sparse gradient exchange (csrc/lgr_sparse.cuh).  Buffer k of step s is rewritten at step s+2; every rank passes the
+    barrier of step s+1 only after its accumulate kernel of step s has finished, so one cross-GPU barrier per step is enough.
+    world == 1 (tests): plain device tensors, no barrier."""
+
+    def __init__(self, device, P, world, group):
+        lib = capi.load()
+        self.world = world
+        n = (int(lib.lgr_sparse_exchange_bytes(P)) + 3) // 4
+        self.ws = torch.empty(int(lib.lgr_sparse_workspace_bytes(P)), dtype=torch.uint8, device=device)
+        if world > 1:
+            import torch.distributed as dist
+            import torch.distributed._symmetric_memory as symm_mem
+            grp = group if group is not None else dist.group.WORLD
+            self.bufs = [symm_mem.empty(n, dtype=torch.float32, device=device) for _ in range(2)]
+            self.hdls = [symm_mem.rendezvous(b, grp.group_name) for b in self.bufs]
+            assert int(self.hdls[0].world_size) == world
+            tables = [[int(p) for p in h.buffer_ptrs] for h in self.hdls]
+        else:
+            self.bufs = [torch.empty(n, dtype=torch.float32, device=device) for _ in range(2)]
+            self.hdls = [None, None]
+            tables = [[b.data_ptr()] for b in self.bufs]
+        for b in self.bufs:
+            b.zero_()
+        for t in tables:
+            assert len(t) == world and all(t) and all(p % 256 == 0 for p in t)
+        self.ptr_tables = [(C.c_void_p * world)(*t) for t in tables]
+        self.turn = 0
+
+    def next(self):
+        self.turn ^= 1
+        return self.turn
+
+
+_sparse_cache = {}
+
+
+def _sparse_exchange(device, P, world, group):
+    """collectively agreed: either every rank gets the peer-mapped buffers or none does (then the dense NCCL exchange is used).
+    LGR_EXCHANGE=dense selects the dense exchange explicitly."""
+    key = (str(device), P, world)
+    if key not in _sparse_cache:
+        xs, ok = None, 1
+        if _os.environ.get("LGR_EXCHANGE", "sparse") != "sparse":
+            ok = 0
+        else:
+            try:
+                xs = _SparseExchange(device, P, world, group)
+            except Exception as ex:  # noqa: BLE001  (no P2P / API drift: the NCCL path still works)
+                print(f"lightgaussian_b200: sparse peer-memory exchange unavailable ({type(ex).__name__}: {ex}); using the dense NCCL exchange", flush=True)
+                ok = 0
+        if world > 1:
+            import torch.distributed as dist
+            flag = torch.tensor([ok], device=device, dtype=torch.int32)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+            ok = int(flag.item())
+        _sparse_cache[key] = xs if ok == 1 else None
+    return _sparse_cache[key]
+
+
+def exchange_info(world):
+    """("sparse-p2p" | "dense-nccl" | "none", rows published by this rank in its last backward or None) -- diagnostics for bench.py"""
+    if world <= 1:
+        return "none", None
+    for (dev, P, w), xs in _sparse_cache.items():
+        if w == world and xs is not None:
+            rows = int(xs.bufs[xs.turn][3:4].view(torch.int32).item())
+            return "sparse-p2p", rows
+    return "dense-nccl", None
+
+
+def _backward_raw_sparse(xs, rs, num_rendered, grad_out_color, xyz, dc, rest, scaling, rotation, opacity, radii, geom, binning, img, world):
+    """View-parallel backward with the sparse exchange: blend backward | flag + scan + per-Gaussian backward of the ~13 % of Gaussians with a
+    non-zero gradient, published in peer-mapped memory | one cross-GPU barrier | every rank reads all views' rows over NVLink and writes the
+    dense, summed leaf gradients (bit-identical on every rank).  No NCCL call, no host synchronisation."""
+    lib = capi.load()
+    device = xyz.device
+    P, M = xyz.size(0), 1 + rest.size(1)
+    H, W = grad_out_color.size(1), grad_out_color.size(2)
+    g2d = torch.empty((P, 3), dtype=torch.float32, device=device)
+    g = [torch.empty_like(t) for t in (xyz, dc, rest, scaling, rotation, opacity)]
+    dpix = _f32c(grad_out_color, "grad_out_color")
+    main = torch.cuda.current_stream(device)
+    k = xs.next()
+    with torch.cuda.device(device):
+        view, keep = _make_view(device, rs.bg, rs.viewmatrix, rs.projmatrix, rs.campos, rs.tanfovx, rs.tanfovy, H, W, rs.scale_modifier,
+                                rs.sh_degree, False, rs.debug)
+        st = lib.lgr_backward_raw_begin(C.byref(view), P, int(num_rendered), radii.data_ptr(), geom.data_ptr(), binning.data_ptr(),
+                                        img.data_ptr(), dpix.data_ptr(), None, main.cuda_stream)
+        capi.check(st, "lgr_backward_raw_begin")
+        params = _raw_struct(xyz, dc, rest, scaling, rotation, opacity)
+        st = lib.lgr_backward_raw_sparse_pack(C.byref(view), P, M, C.byref(params), radii.data_ptr(), geom.data_ptr(), xs.bufs[k].data_ptr(),
+                                              xs.ws.data_ptr(), g2d.data_ptr(), main.cuda_stream)
+        capi.check(st, "lgr_backward_raw_sparse_pack")
+        if world > 1:
+            xs.hdls[k].barrier(channel=0)          # every rank's rows of this step are published
+        grads = _raw_grads_struct(*g)
+        st = lib.lgr_backward_raw_sparse_accumulate(P, M, int(rs.sh_degree), world, xs.ptr_tables[k], xyz.data_ptr(), C.byref(grads),
+                                                    main.cuda_stream)
+        capi.check(st, "lgr_backward_raw_sparse_accumulate")
+    return g, g2d
 
 
 def _exchange_chunks(P):
