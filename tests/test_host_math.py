@@ -82,3 +82,16 @@ def test_backward_math_matches_oracle(lib):
                                _p(out["dL_dmeans3D"]), _p(out["dL_dcov3D"]), _p(out["dL_dsh"]), _p(out["dL_dscales"]), _p(out["dL_drotations"]))
     for k in out:
         assert rel_inf(out[k], b[k]) < 2e-5, (k, rel_inf(out[k], b[k]))
+
+
+def test_exchange_ranges_cover_all_gaussians_on_block_boundaries(monkeypatch):
+    """host logic of the view-parallel exchange: ranges handed to lgr_backward_raw_end_range start at multiples of 256 and tile [0, P)"""
+    from lightgaussian_b200 import rasterizer
+    for chunks in ("1", "2", "4", "7"):
+        monkeypatch.setenv("LGR_EXCHANGE_CHUNKS", chunks)
+        for P in (1, 255, 256, 257, 1000, 65536, 3_000_000):
+            r = rasterizer._exchange_chunks(P)
+            assert r[0][0] == 0 and sum(n for _, n in r) == P and len(r) <= int(chunks)
+            assert all(f % 256 == 0 and n > 0 for f, n in r)
+            assert all(r[k][0] + r[k][1] == r[k + 1][0] for k in range(len(r) - 1))
+    assert rasterizer.exchange_info(1) == ("none", None)
