@@ -64,3 +64,26 @@ print("ok")
     env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(ROOT, "dropin"), ROOT, REF]))
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="needs the reference checkout (build container only)")
+def test_reference_scripts_import_unmodified_against_the_dropins():
+    """prune_finetune.py, distill_train.py, train_densify_prune.py, render.py, render_video.py, prune.py and metrics.py -- the callers of the hot
+    path -- import with the documented PYTHONPATH order: every `from gaussian_renderer / diff_gaussian_rasterization /
+    utils.loss_utils / vectree.utils / scene import ...` they do resolves (to ours where we replace it, to the reference's file otherwise)."""
+    code = r"""
+import sys, importlib
+sys.argv = ["x"]
+for m in ["prune_finetune", "distill_train", "train_densify_prune", "render", "render_video", "prune", "metrics"]:
+    mod = importlib.import_module(m)
+    assert mod.__file__.startswith("/root/reference/"), mod.__file__
+import prune_finetune, metrics
+import lightgaussian_b200.renderer as ours, lightgaussian_b200.loss as ours_loss
+assert prune_finetune.render is ours.render
+assert prune_finetune.l1_loss.__module__ == "utils.loss_utils" and prune_finetune.l1_loss.__code__.co_filename.startswith(%r)
+assert metrics.ssim.__code__.co_filename.startswith(%r)
+print("ok")
+""" % (os.path.join(ROOT, "dropin"), os.path.join(ROOT, "dropin"))
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(ROOT, "dropin"), ROOT, REF]))
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600, cwd="/tmp")
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
