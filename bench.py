@@ -37,7 +37,13 @@ def parse_args():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
-    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--impl", choices=["ours", "reference", "reference-kernels"], default="ours",
+                    help="reference = the UNMODIFIED reference stack from baseline/_ref (its pybind extension built from RAST/setup.py, its "
+                         "gaussian_renderer.render, its GaussianModel, its l1_loss); reference-kernels = the reference's kernels behind our "
+                         "own harness (oracle/_ref shim)")
+    ap.add_argument("--mode", choices=["train", "distill"], default="train",
+                    help="train = the headline step (render + L1 + backward); distill = one distill_train.py iteration "
+                         "(student M=9 strided leaf + teacher M=16 renders, 0.8 L1 + 0.2 DSSIM, backward, AdamW step)")
     ap.add_argument("--P", type=int, default=3_000_000, help="number of Gaussians (default: the 3M workload)")
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
@@ -172,6 +178,35 @@ def make_reference_render():
     return render
 
 
+def make_stock_reference(raw, dev):
+    """The reference's own public path, UNMODIFIED: `gaussian_renderer.render` + `scene.gaussian_model.GaussianModel`
+    + the pybind extension `diff_gaussian_rasterization._C` built from RAST/setup.py (rasterize_points.cu:46-299), all from baseline/_ref
+    (staged by baseline/stage_reference.py).  Returns (render_fn, gaussians, l1_loss, AdamW-factory) or None when it is not staged."""
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    tree = os.path.join(ref, "LightGaussian")
+    ext = os.path.join(ref, "diff_gaussian_rasterization")
+    if not (os.path.isfile(os.path.join(tree, "gaussian_renderer", "__init__.py")) and os.path.isdir(ext)
+            and any(f.startswith("_C") and f.endswith(".so") for f in os.listdir(ext))):
+        return None
+    for p_ in (tree, os.path.join(ref, "shims"), ref):
+        sys.path.insert(0, p_)
+    for name in [m for m in sys.modules if m.split(".")[0] in ("gaussian_renderer", "diff_gaussian_rasterization", "utils", "scene")]:
+        del sys.modules[name]
+    import diff_gaussian_rasterization as dgr
+    import gaussian_renderer as gr
+    from scene.gaussian_model import GaussianModel
+    from utils.loss_utils import l1_loss
+    assert dgr.__file__.startswith(ref) and gr.__file__.startswith(tree), (dgr.__file__, gr.__file__)
+    from torch import nn
+    g = GaussianModel(3)
+    leaf = lambda a: nn.Parameter(torch.from_numpy(np.ascontiguousarray(a)).float().to(dev).requires_grad_(True))  # noqa: E731
+    g._xyz, g._features_dc, g._features_rest = leaf(raw["xyz"]), leaf(raw["features_dc"]), leaf(raw["features_rest"])
+    g._scaling, g._rotation, g._opacity = leaf(raw["scaling"]), leaf(raw["rotation"]), leaf(raw["opacity"])
+    g.active_sh_degree = 3
+    g.parameters = lambda: [g._xyz, g._features_dc, g._features_rest, g._scaling, g._rotation, g._opacity]
+    return gr.render, g, l1_loss
+
+
 # ------------------------------------------------------------------------------------------------
 def cpu_oracle_sample(scene, cam, W, H):
     """the CPU port (oracle/lgo.c, single thread) on ONE view of the same workload: forward + backward."""
@@ -207,10 +242,102 @@ def make_torch_reference_loss(dev):
 
 
 
+def main_distill(args, rank, world, dev):
+    """--mode distill: one distill_train.py iteration per step and rank (distill_train.py:124-166 with the C4 flags --new_max_sh 2
+    --enable_covariance): student render (M = 9, _features_rest the NON-contiguous [P,8,3] view onedownSHdegree() leaves,
+    scene/gaussian_model.py:129-136; opacity frozen), teacher render (M = 16, leaves require grad, image detached),
+    0.8 L1 + 0.2 (1 - SSIM), backward, AdamW.step, zero_grad.  N > 1: each rank takes its own camera, student gradients summed."""
+    from lightgaussian_b200 import parallel
+    from lightgaussian_b200.model import GaussianParams, TorchCamera, pipeline_params
+    from lightgaussian_b200.synth import make_scene, make_cameras
+    P, W, H = args.P, args.width, args.height
+    scene = make_scene(P, sh_degree=3, seed=0)
+    cams = [TorchCamera(c, dev) for c in make_cameras(args.cams, W, H)]
+    bg = torch.zeros(3, device=dev)
+    pipe = pipeline_params()
+    names = ["_xyz", "_features_dc", "_features_rest", "_opacity", "_scaling", "_rotation"]
+    lrs = [1.6e-4, 2.5e-3, 2.5e-3 / 20, 0.05, 0.005, 0.001]
+    launches0 = 0
+    if args.impl == "ours":
+        from lightgaussian_b200 import capi, loss as fused_loss, optim as fused_optim, rasterizer
+        from lightgaussian_b200.renderer import render as render_fn
+        capi.load()
+        teacher = GaussianParams(scene["raw"], 3, dev)
+        student = GaussianParams(scene["raw"], 3, dev)
+        student._features_rest = student._features_rest.clone().detach()[:, :8, :]      # onedownSHdegree(), verbatim
+        student._features_rest.requires_grad = True
+        student.max_sh_degree = student.active_sh_degree = 2
+        student._opacity.requires_grad = False                                           # no --enable_opacity
+        loss_fn = lambda x, y: fused_loss.l1_ssim_loss(x, y, 0.2)  # noqa: E731
+        opt = fused_optim.FusedAdamW([{"params": [getattr(student, n)], "lr": lr, "name": n} for n, lr in zip(names, lrs)], lr=0.0, eps=1e-15)
+        if world > 1:
+            parallel.enable_gradient_exchange(world)
+        kind = "fused kernels (strided student leaf read and updated in place)"
+    else:
+        stock = make_stock_reference(scene["raw"], dev)
+        if stock is None:
+            print(json.dumps({"impl": args.impl, "unavailable": "baseline/_ref (stock reference stack) is not staged"}))
+            return 0
+        render_fn, teacher, _ = stock
+        import copy
+        student = copy.deepcopy(teacher)
+        student.max_sh_degree = 2
+        student.onedownSHdegree()
+        student._opacity.requires_grad = False
+        torch_loss = make_torch_reference_loss(dev)
+        loss_fn = torch_loss
+        opt = torch.optim.AdamW([{"params": [getattr(student, n)], "lr": lr, "name": n} for n, lr in zip(names, lrs)], lr=0.0, eps=1e-15)
+        kind = "stock reference stack (baseline/_ref) + torch loss composition + torch.optim.AdamW"
+    assert not student._features_rest.is_contiguous()
+
+    def step(k):
+        cam = cams[(k * world + rank) % len(cams)]
+        s_img = render_fn(cam, student, pipe, bg)["render"]
+        t_img = render_fn(cam, teacher, pipe, bg)["render"].detach()
+        loss_fn(s_img, t_img).backward()
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+
+    for k in range(args.warmup):
+        step(k)
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+    if args.impl == "ours":
+        launches0 = capi.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(args.steps):
+        step(args.warmup + k)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+    ms = float(ms.item())
+    if rank == 0:
+        line = {"metric": "distillation iterations/sec at 3M Gaussians 1080p (student SH2 + teacher SH3, views sharded over GPUs)",
+                "value": args.steps * world / (ms * 1e-3), "unit": "views/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"{P} Gaussians, {W}x{H}, distill_train.py iteration: student SH degree 2 (strided [P,8,3] leaf) + teacher SH degree 3, "
+                                       "0.8 L1 + 0.2 DSSIM, backward, AdamW", "gaussians": P, "resolution": [W, H], "cameras": len(cams)},
+                "run": {"views_per_step": world, "path": kind},
+                "gpu_launches": (capi.launch_count() - launches0) if args.impl == "ours" else 0}
+        if args.impl != "ours":
+            line["impl"] = args.impl
+        elif world > 1:
+            line["run"]["unfused_exchange_calls"] = rasterizer.unfused_exchange_calls()
+        print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+    return 0
+
+
 def main():
     args = parse_args()
     from lightgaussian_b200 import parallel
-    if args.impl == "reference":
+    if args.impl != "ours":
         # the reference is single-GPU (utils/general_utils.py:151 pins cuda:0): under torchrun rank 0 alone runs it, the other
         # ranks exit without joining any process group
         if int(os.environ.get("RANK", "0")) != 0:
@@ -221,6 +348,8 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU path in the product)"
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
+    if args.mode == "distill":
+        return main_distill(args, rank, world, dev)
 
     from lightgaussian_b200.model import GaussianParams, TorchCamera, pipeline_params
     from lightgaussian_b200.synth import make_scene, make_cameras
@@ -229,6 +358,11 @@ def main():
     scene = make_scene(P, sh_degree=3, seed=0)
     cams_np = make_cameras(args.cams, W, H)
     pc = GaussianParams(scene["raw"], 3, dev)
+    stock = None
+    if args.impl == "reference":
+        stock = make_stock_reference(scene["raw"], dev)
+        if stock is not None:
+            pc = stock[1]           # the reference's own GaussianModel holds the parameters
     cams = [TorchCamera(c, dev) for c in cams_np]
     bg = torch.zeros(3, device=dev)
     pipe = pipeline_params()
@@ -261,9 +395,11 @@ def main():
         from lightgaussian_b200.renderer import render as render_fn
         capi.load()
         kind = None
+    elif stock is not None:
+        render_fn, kind = stock[0], "reference"
     else:
         render_fn = make_reference_render()
-        kind = "reference"
+        kind = "reference-kernels"
         if render_fn is None:
             kind = "port"
 
@@ -272,6 +408,8 @@ def main():
     step_loss = None
     if args.impl == "ours" and os.environ.get("LGR_BENCH_TORCH_L1", "0") != "1":
         from lightgaussian_b200.loss import l1_loss as step_loss
+    elif stock is not None:
+        step_loss = stock[2]        # utils/loss_utils.py:18-19, the reference's own
 
     def view_index(step):
         return (step * world + rank) % len(cams)
@@ -335,6 +473,46 @@ def main():
         if world > 1:
             torch.distributed.barrier()
 
+    def exchange_self_check():
+        """N > 1, outside every timed region: on a 20k-Gaussian scene each rank renders ITS view and runs the exchanging backward; the
+        summed leaf gradients must be (a) bit-identical on every rank -- replicas cannot drift -- and (b) within 1e-3 of the serial
+        sum of the per-view gradients, which every rank recomputes locally with the exchange switched off.  Raises on failure, so a
+        driver-run SCALE step cannot report a number for a broken exchange."""
+        from lightgaussian_b200.synth import make_scene as mk_scene, make_cameras as mk_cams
+        Ws, Hs = 320, 240
+        sc = mk_scene(20000, sh_degree=3, seed=3, scale_mult=1.5)
+        cs = [TorchCamera(c, dev) for c in mk_cams(world, Ws, Hs)]
+        tg = [torch.rand(3, Hs, Ws, generator=torch.Generator().manual_seed(100 + r)).to(dev) for r in range(world)]
+        ps = GaussianParams(sc["raw"], 3, dev)
+
+        def grads_of(view):
+            for q in ps.parameters():
+                q.grad = None
+            train_view(render_fn, cs[view], ps, pipe, bg, tg[view], step_loss)
+            return [q.grad.detach().clone() for q in ps.parameters()]
+        gx = grads_of(rank)                                   # exchanged: already the sum over all ranks' views
+        parallel.enable_gradient_exchange(1)                  # serial reference on this rank
+        try:
+            serial = None
+            for v_ in range(world):
+                gv = grads_of(v_)
+                serial = gv if serial is None else [a + b for a, b in zip(serial, gv)]
+        finally:
+            parallel.enable_gradient_exchange(world)
+        worst, equal = 0.0, True
+        for a, b in zip(gx, serial):
+            worst = max(worst, float((a - b).abs().max() / b.abs().max().clamp_min(1e-20)))
+            ref0 = a.clone()
+            torch.distributed.broadcast(ref0, src=0)
+            equal = equal and bool(torch.equal(ref0, a))
+        flags = torch.tensor([1.0 if equal else 0.0, -worst], device=dev)
+        torch.distributed.all_reduce(flags, op=torch.distributed.ReduceOp.MIN)
+        res = {"bit_equal_across_ranks": bool(flags[0].item() == 1.0), "max_rel_err_vs_serial_sum": float(-flags[1].item()),
+               "scene": "20000 Gaussians, 320x240, one view per rank", "unfused_exchange_calls": rasterizer.unfused_exchange_calls()}
+        if not res["bit_equal_across_ranks"] or not res["max_rel_err_vs_serial_sum"] <= 1e-3:
+            raise RuntimeError(f"gradient exchange self-check FAILED: {res}")
+        return res
+
     def timed(fn, steps, sampler=None):
         barrier()
         torch.cuda.synchronize()
@@ -366,7 +544,7 @@ def main():
         return float(ms.item()), clocks
 
     # ---------------- the reference arm when its kernels could not be built: CPU port ----------------
-    if args.impl == "reference" and kind == "port":
+    if args.impl != "ours" and kind == "port":
         v, dt = cpu_oracle_sample(scene, cams_np[0], W, H)
         line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": 1, "steps": 1, "warmup": 0,
                 "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -401,6 +579,8 @@ def main():
         h2d = 3 * H * W * 4 + (16 + 16 + 3) * 4
         e2e = {"value": views / (ms_e * 1e-3), "unit": UNIT, "ms_per_step": ms_e / args.steps, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": 4}
+
+    exchange_check = exchange_self_check() if fused_exchange else None
 
     # ---------------- roofline of the dominant kernel (rank 0, our arm) ----------------
     roofline, stages = None, None
@@ -495,7 +675,7 @@ def main():
     # ---------------- whole training iteration (rows N2 + N3 included): render -> L1+DSSIM -> backward -> AdamW -> zero_grad ------
     # prune_finetune.py:144-166,287-289.  Reported beside the headline (whose step definition stays render+L1+backward).
     iteration_pass = None
-    if world == 1 and not args.no_roofline:
+    if not args.no_roofline and (world == 1 or args.impl == "ours"):
         names = ["_xyz", "_features_dc", "_features_rest", "_opacity", "_scaling", "_rotation"]
         lrs = [1.6e-4, 2.5e-3, 2.5e-3 / 20, 0.05, 0.005, 0.001]                       # arguments/__init__.py OptimizationParams
         groups = lambda: [{"params": [getattr(pc, n)], "lr": lr, "name": n} for n, lr in zip(names, lrs)]  # noqa: E731
@@ -510,18 +690,21 @@ def main():
                 opt.zero_grad(set_to_none=True)
             return it
         zero_grads()
-        arms = {"torch_loss_and_adamw": (torch_loss, torch.optim.AdamW(groups(), lr=0.0, eps=1e-15))}
+        arms = {}
+        if world == 1:
+            arms["torch_loss_and_adamw"] = (torch_loss, torch.optim.AdamW(groups(), lr=0.0, eps=1e-15))
         if args.impl == "ours":
             from lightgaussian_b200 import loss as fused_loss, optim as fused_optim
             arms["fused_loss_and_adamw"] = (lambda x, y: fused_loss.l1_ssim_loss(x, y, 0.2), fused_optim.FusedAdamW(groups(), lr=0.0, eps=1e-15))
-        iteration_pass = {"what": "render + (0.8 L1 + 0.2 DSSIM) + backward + AdamW.step + zero_grad, iterations/s", "unit": "iterations/s"}
+        iteration_pass = {"what": "render + (0.8 L1 + 0.2 DSSIM) + backward (+ gradient exchange when N > 1) + AdamW.step + zero_grad; views/s over all ranks",
+                          "unit": "views/s"}
         nit = min(args.steps, 10)
         for name, (lf, opt) in arms.items():
             fn = make_iter(lf, opt)
             for s_ in range(3):
                 fn(s_)
             t_it, _ = timed(fn, nit)
-            iteration_pass[name] = nit / (t_it * 1e-3)
+            iteration_pass[name] = nit * world / (t_it * 1e-3)
             if name == "fused_loss_and_adamw":
                 # device time of the N2/N3 kernels inside this iteration (library CUDA events), against the HBM peak
                 peak_rows = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]) \
@@ -593,9 +776,11 @@ def main():
             cpu_baseline = {"value": v_cpu, "unit": UNIT, "cores": 1, "kind": "port",
                             "sample": f"1 view forward+backward of the same workload ({dt:.1f} s), oracle/lgo.c single thread; host has {os.cpu_count()} cores"}
         else:
+            how = ("its stock public path: gaussian_renderer.render + GaussianModel + the pybind extension built from RAST/setup.py (baseline/_ref)"
+                   if kind == "reference" else
+                   "its kernels behind our harness (oracle/_ref: forward.cu/backward.cu/rasterizer_impl.cu compiled unmodified for sm_100a)")
             cpu_baseline = {"value": value, "unit": UNIT, "cores": 0, "kind": "reference",
-                            "sample": "the reference has NO CPU implementation of this path: this arm times its own CUDA kernels "
-                                      "(oracle/_ref: forward.cu/backward.cu/rasterizer_impl.cu compiled unmodified for sm_100a) on the same GPU, "
+                            "sample": f"the reference has NO CPU implementation of this path: this arm times {how} on the same GPU, "
                                       f"same steps; host has {os.cpu_count()} cores"}
 
     if args.impl == "ours" and os.environ.get("LGR_EXCHANGE_TIMING", "0") == "1":
@@ -615,23 +800,29 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
+            # `config` identifies the WORKLOAD only, so that both arms (and every N) print the same object; how this run executed it
+            # (ranks, exchange, which code path) is under "run"
             "config": {"workload": f"{P} Gaussians SH degree 3, {W}x{H}, {len(cams)} synthetic cameras (Fibonacci sphere r=3), "
-                                   "step = render()+L1+backward to raw leaves (L1 = each stack's own l1_loss)" + (" + 1 NCCL all-reduce of gradients" if world > 1 else ""),
-                       "gaussians": P, "resolution": [W, H], "views_per_step": world, "parallelism": f"view-parallel x{world}",
-                       "l2_policy": "inputs larger than L2 (>=0.7 GB of parameters streamed per step)",
-                       "grad_exchange": ("none" if world == 1 else "DISABLED (diagnostic run, not a valid measurement)" if args.no_exchange else
-                                         (xdesc if fused_exchange else "dense all-reduce")),
-                       "grad_exchange_bytes_per_rank": 0 if world == 1 else (xbytes if fused_exchange else grad_bytes),
-                       "fused_activations": bool(args.impl == "ours" and os.environ.get("LGR_FUSED", "1") != "0")},
+                                   "step = one training view per GPU: render() + L1 + backward to the six raw leaves",
+                       "gaussians": P, "resolution": [W, H], "cameras": len(cams),
+                       "l2_policy": "inputs larger than L2 (>=0.7 GB of parameters streamed per step)"},
+            "run": {"views_per_step": world, "parallelism": f"view-parallel x{world}", "l1": "each stack's own l1_loss",
+                    "grad_exchange": ("none" if world == 1 else "DISABLED (diagnostic run, not a valid measurement)" if args.no_exchange else
+                                      (xdesc if fused_exchange else "dense all-reduce")),
+                    "grad_exchange_bytes_per_rank": 0 if world == 1 else (xbytes if fused_exchange else grad_bytes),
+                    "path": ("fused activations + raw-leaf kernels" if (args.impl == "ours" and os.environ.get("LGR_FUSED", "1") != "0") else
+                             "reference-compatible API path" if args.impl == "ours" else kind)},
             "clocks": clocks, "gpu_launches": launches,
         }
-        if args.impl == "reference":
-            line["impl"] = "reference"
+        if args.impl != "ours":
+            line["impl"] = args.impl
             line["e2e"] = {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
             if e2e:
                 line["e2e_host_buffers"] = e2e
         else:
             line["e2e"] = e2e
+        if exchange_check:
+            line["exchange_check"] = exchange_check
         if roofline:
             line["roofline"] = roofline
             line["stages"] = stages

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define LGR_ABI_VERSION 1
+#define LGR_ABI_VERSION 2
 
 /* status codes */
 #define LGR_OK 0
@@ -109,6 +109,10 @@ typedef struct lgr_raw_params {
     const float* scaling;       /* [P,3] log-scale         -> exp        */
     const float* rotation;      /* [P,4] raw quaternion    -> normalize  */
     const float* opacity;       /* [P,1] logit             -> sigmoid    */
+    int32_t features_rest_row_stride; /* floats between consecutive rows of features_rest; 0 = dense, i.e. (M-1)*3.
+                                       * A larger value describes a row-strided view such as the distillation student's
+                                       * _features_rest[:, :8, :] of a [P,15,3] tensor (scene/gaussian_model.py:129-136):
+                                       * stride 45, 24 floats used.  The storage must hold P*stride floats from the pointer. */
 } lgr_raw_params;
 
 typedef struct lgr_raw_grads { /* dL/d(leaf), same shapes, fully written */
@@ -207,6 +211,8 @@ typedef struct lgr_adamw_tensor {
     int64_t numel;
     double lr;
     double step;
+    int64_t row_elems;        /* 0: param is contiguous.  Otherwise param is a row-strided view: element e lives at     */
+    int64_t param_row_stride; /* param[(e / row_elems) * param_row_stride + e % row_elems]; grad and moments stay dense */
 } lgr_adamw_tensor;
 int lgr_adamw_step(int n_tensors, const lgr_adamw_tensor* tensors, double beta1, double beta2, double eps, double weight_decay,
                    void* cuda_stream);

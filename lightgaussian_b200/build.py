@@ -20,12 +20,30 @@ NVCC_FLAGS = [
 ]
 
 
+HASH_PATH = LIB_PATH + ".srchash"
+
+
+def _source_hash() -> str:
+    """content hash of every source/header and the compiler flags (mtimes do not survive the snapshot copy to the GPU box)"""
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for d in sorted(os.path.join(CSRC, s) for s in SOURCES + HEADERS):
+        if os.path.exists(d):
+            with open(d, "rb") as f:
+                h.update(os.path.basename(d).encode() + b"\0" + f.read())
+    return h.hexdigest()
+
+
 def _stale() -> bool:
-    if not os.path.exists(LIB_PATH):
+    """True when liblgrast.so is missing or was not built from the sources as they are now."""
+    if not os.path.exists(LIB_PATH) or not os.path.exists(HASH_PATH):
         return True
-    t = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS]
-    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+    with open(HASH_PATH) as f:
+        return f.read().strip() != _source_hash()
+
+
+def have_nvcc() -> bool:
+    return bool(shutil.which("nvcc")) or os.path.exists("/usr/local/cuda/bin/nvcc")
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
@@ -36,11 +54,15 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: cannot build liblgrast.so (and there is no CPU fallback)")
     os.makedirs(LIB_DIR, exist_ok=True)
-    tmp = LIB_PATH + ".tmp"
+    tmp = LIB_PATH + f".tmp{os.getpid()}"
     cmd = [nvcc] + NVCC_FLAGS + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", tmp]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd))
+    digest = _source_hash()
     subprocess.check_call(cmd)
     os.replace(tmp, LIB_PATH)
+    with open(HASH_PATH + ".tmp", "w") as f:
+        f.write(digest + "\n")
+    os.replace(HASH_PATH + ".tmp", HASH_PATH)
     return LIB_PATH

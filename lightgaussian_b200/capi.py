@@ -15,6 +15,7 @@ import torch
 from . import build as _build
 
 LGR_OK = 0
+ABI_VERSION = 2   # LGR_ABI_VERSION of include/lgrast.h this binding was written against
 
 
 class LgrView(C.Structure):
@@ -27,21 +28,24 @@ class LgrView(C.Structure):
     ]
 
 
+_SIX_LEAVES = [("xyz", C.c_void_p), ("features_dc", C.c_void_p), ("features_rest", C.c_void_p), ("scaling", C.c_void_p),
+               ("rotation", C.c_void_p), ("opacity", C.c_void_p)]
+
+
 class LgrRawParams(C.Structure):
-    """struct lgr_raw_params / lgr_raw_grads (same layout: six pointers)"""
-    _fields_ = [("xyz", C.c_void_p), ("features_dc", C.c_void_p), ("features_rest", C.c_void_p), ("scaling", C.c_void_p),
-                ("rotation", C.c_void_p), ("opacity", C.c_void_p)]
+    """struct lgr_raw_params: six leaf pointers + the row stride (floats) of features_rest (0 = dense)"""
+    _fields_ = _SIX_LEAVES + [("features_rest_row_stride", C.c_int32)]
 
 
 class LgrRawGrads(C.Structure):
-    """struct lgr_raw_grads: the six leaf gradients + the optional compact dL/dRGB factor"""
-    _fields_ = LgrRawParams._fields_ + [("rgb", C.c_void_p)]
+    """struct lgr_raw_grads: the six (dense) leaf gradients + the optional compact dL/dRGB factor"""
+    _fields_ = _SIX_LEAVES + [("rgb", C.c_void_p)]
 
 
 class LgrAdamwTensor(C.Structure):
     """struct lgr_adamw_tensor"""
     _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
-                ("numel", C.c_int64), ("lr", C.c_double), ("step", C.c_double)]
+                ("numel", C.c_int64), ("lr", C.c_double), ("step", C.c_double), ("row_elems", C.c_int64), ("param_row_stride", C.c_int64)]
 
 
 class LgrCompactTensor(C.Structure):
@@ -67,11 +71,13 @@ def load():
     with _lib_lock:
         if _lib is not None:
             return _lib
+        # rebuild when the sources are newer than the binary and nvcc is here (build_library returns early when up to date);
+        # on a box without nvcc the shipped binary is used as is
         path = _build.LIB_PATH
-        if not os.path.exists(path):
+        if not os.path.exists(path) or (_build.have_nvcc() and _build._stale()):
             path = _build.build_library()
         lib = C.CDLL(path)
-        if lib.lgr_abi_version() != 1:
+        if lib.lgr_abi_version() != ABI_VERSION:
             raise RuntimeError("liblgrast.so ABI version mismatch")
         vp, i32 = C.c_void_p, C.c_int
         fwd_common = [C.POINTER(LgrView), i32, i32] + [vp] * 7 + [ALLOC_FN, vp, ALLOC_FN, vp, ALLOC_FN, vp]

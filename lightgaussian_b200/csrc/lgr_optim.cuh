@@ -33,6 +33,8 @@ struct AdamTable {
     float* m[OPT_MAX_TENSORS];
     float* v[OPT_MAX_TENSORS];
     long long n[OPT_MAX_TENSORS];
+    int row_elems[OPT_MAX_TENSORS];         // 0 = contiguous parameter; else elements per row of a row-strided parameter view
+    int row_stride[OPT_MAX_TENSORS];        // its row stride in elements
     int chunk_start[OPT_MAX_TENSORS + 1];   // prefix sum of ceil(n / OPT_CHUNK)
     float decay[OPT_MAX_TENSORS];           // 1 - lr*wd
     float neg_step[OPT_MAX_TENSORS];        // -(lr / (1 - beta1^t))
@@ -99,7 +101,20 @@ __global__ void __launch_bounds__(256) adamw_multi_kernel(const AdamTable t)
     const float decay = t.decay[k], neg_step = t.neg_step[k], bc2 = t.bc2_sqrt[k];
     const bool vec = ((reinterpret_cast<uintptr_t>(P) | reinterpret_cast<uintptr_t>(G) | reinterpret_cast<uintptr_t>(M) |
                        reinterpret_cast<uintptr_t>(V)) & 15) == 0;
-    if (vec && base + OPT_CHUNK <= n) {
+    const int re = t.row_elems[k];
+    if (re > 0) {  // row-strided parameter (the distillation student's _features_rest[:, :8, :]): gradient and moments are dense
+        const long long rs = t.row_stride[k];
+#pragma unroll 4
+        for (int i = threadIdx.x; i < OPT_CHUNK; i += 256) {
+            const long long e = base + i;
+            if (e >= n) break;
+            const long long row = e / re;
+            float* pp = P + row * rs + (e - row * re);
+            float p = *pp, m = M[e], v = V[e];
+            adamw_element(p, G[e], m, v, decay, neg_step, bc2, t.w1, t.beta2, t.w2, t.eps);
+            *pp = p; M[e] = m; V[e] = v;
+        }
+    } else if (vec && base + OPT_CHUNK <= n) {
         float4 p4[4], g4[4], m4[4], v4[4];
 #pragma unroll
         for (int u = 0; u < 4; u++) {

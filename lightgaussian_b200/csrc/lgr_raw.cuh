@@ -83,12 +83,17 @@ struct RawArgs {
     const float* proj;
     const float* campos;
     int prefiltered;
+    int rest_stride;  // floats between consecutive rows of `rest` (>= (M-1)*3; equal when the leaf is dense)
 };
 
-// dynamic shared memory: 8 warp slices [32*nrest floats rest | 32*3 floats dc], then 8 mbarriers, then camera (36 floats)
-__host__ __device__ inline size_t raw_smem_bytes(int M) { return (size_t)8 * 128 * ((M - 1) * 3 + 3) + 64 + 36 * 4; }
+// dynamic shared memory: 8 warp slices [32*stride floats rest | 32*3 floats dc], then 8 mbarriers, then camera (36 floats).
+// `stride` = floats per staged features_rest row: (M-1)*3 for a dense leaf, the leaf's row stride for a row-strided view
+// (the distillation student's _features_rest[:, :8, :], scene/gaussian_model.py:129-136, has stride 45 for 24 used floats).
+__host__ __device__ inline size_t raw_smem_bytes_stride(int stride) { return (size_t)8 * 128 * (stride + 3) + 64 + 36 * 4; }
+__host__ __device__ inline size_t raw_smem_bytes(int M) { return raw_smem_bytes_stride((M - 1) * 3); }
 
-// Stage one warp's SH rows.  `first` = index of the warp's first Gaussian, `n` = valid Gaussians in the warp (<= 32).
+// Stage one warp's SH rows.  `first` = index of the warp's first Gaussian, `n` = valid Gaussians in the warp (<= 32),
+// `nrest` = floats per row of `rest` in memory (the row stride: whole rows are staged, lanes read theirs at that stride).
 __device__ __forceinline__ bool warp_stage_sh_begin(const float* __restrict__ rest, const float* __restrict__ dc, int nrest, int first, int n,
                                                     float* s_rest, float* s_dc, uint64_t* bar, int lane)
 {
@@ -110,7 +115,7 @@ __device__ __forceinline__ bool warp_stage_sh_begin(const float* __restrict__ re
 __global__ void __launch_bounds__(256) preprocess_raw_kernel(RawArgs a, int* __restrict__ radii, GeometryState g)
 {
     extern __shared__ __align__(128) unsigned char dyn_smem[];
-    const int nrest = (a.M - 1) * 3;
+    const int nrest = a.rest_stride;   // floats per staged row (the leaf's row stride)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* s_rest = reinterpret_cast<float*>(dyn_smem) + (size_t)warp * 32 * (nrest + 3);
     float* s_dc = s_rest + 32 * nrest;
@@ -219,6 +224,7 @@ struct RawBackArgs {
     float* d_rotation;
     float* d_opacity;
     float* dL_dmeans2D;
+    int rest_stride;  // floats between consecutive rows of `rest` ((M-1)*3 when dense); gradients are always dense
     int block0;    // first 256-Gaussian block this launch covers (ranged launches of the view-parallel exchange)
     float* d_rgb;  // optional [P,3]: clamp-masked dL/dRGB (compact SH gradient factor); when set and d_rest == NULL the dense SH rows are not written
 };
@@ -252,8 +258,10 @@ __global__ void __launch_bounds__(256) preprocess_backward_raw_kernel(RawBackArg
     const bool valid = lane < n;
     const bool vis = valid && a.radii[i] > 0;
     const bool any_vis = __any_sync(FULL, vis);
-    // the SH values are only needed for the view-direction term (degree >= 1)
-    const bool need_sh = any_vis && a.D > 0;
+    // the SH values are only needed for the view-direction term (degree >= 1).  A row-strided leaf (rest_stride != nrest) is
+    // not staged: the shared-memory slice holds the DENSE gradient rows, so its lanes read their coefficients from global memory
+    const bool strided = a.rest_stride != nrest;
+    const bool need_sh = any_vis && a.D > 0 && !strided;
     bool bulk = false;
     if (need_sh) bulk = warp_stage_sh_begin(a.rest, a.dc, nrest, first, n, s_rest, s_dc, &bars[warp], lane);
 
@@ -297,7 +305,16 @@ __global__ void __launch_bounds__(256) preprocess_backward_raw_kernel(RawBackArg
     float* dd = s_dc + lane * 3;
     if (valid) {
         if (vis) {
-            if (a.D > 0) {
+            if (a.D > 0 && strided) {
+                const float* gr = a.rest + si * a.rest_stride;
+                const float* gd = a.dc + si * 3;
+                lgr::sh_backward(a.D, [&](int k) { return k < 3 ? __ldg(gd + k) : __ldg(gr + k - 3); },
+                                 [&](int k, int c, float val) {
+                                     if (k == 0) dd[c] = val;
+                                     else rr[3 * (k - 1) + c] = val;
+                                 },
+                                 x, y, z, cam, dRGB, dmean);
+            } else if (a.D > 0) {
                 lgr::sh_backward(a.D, [&](int k) { return k < 3 ? dd[k] : rr[k - 3]; },
                                  [&](int k, int c, float val) {
                                      if (k == 0) dd[c] = val;

@@ -88,7 +88,6 @@ __global__ void __launch_bounds__(256) preprocess_backward_sparse_kernel(RawBack
     if (t >= (int)hdr[3]) return;
     const int i = idx[t];
     const size_t si = (size_t)i;
-    const int nrest = (a.M - 1) * 3;
 
     float dmean[3] = {0.f, 0.f, 0.f}, dscale[3], dq[4], dRGB[3];
     const float4 co = a.conic_opacity[si];
@@ -115,7 +114,7 @@ __global__ void __launch_bounds__(256) preprocess_backward_sparse_kernel(RawBack
     const float o = co.w;
     const float dop = (g2.dop * (1.0f - o)) * o;
     if (a.D > 0) {  // view-direction term of dL/dmean3D; the SH gradient itself is rebuilt from dRGB by the accumulate kernel
-        const float* rr = a.rest + si * nrest;
+        const float* rr = a.rest + si * a.rest_stride;
         const float* dd = a.dc + si * 3;
         lgr::sh_backward(a.D, [&](int k) { return k < 3 ? dd[k] : rr[k - 3]; }, [](int, int, float) {}, x, y, z, cam, dRGB, dmean);
     }

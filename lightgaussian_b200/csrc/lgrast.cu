@@ -927,6 +927,14 @@ namespace {
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
+// row stride (floats) of the features_rest leaf: 0 in the struct means dense
+inline int raw_rest_stride(const lgr_raw_params* raw, int M) { return raw->features_rest_row_stride > 0 ? raw->features_rest_row_stride : (M - 1) * 3; }
+inline bool raw_rest_stride_ok(const lgr_raw_params* raw, int M)
+{
+    const int s = raw->features_rest_row_stride;
+    return s == 0 || (s >= (M - 1) * 3 && s <= 256);
+}
+
 struct PinnedInt {
     int* p = nullptr;
     ~PinnedInt() { if (p) cudaFreeHost(p); }
@@ -957,6 +965,10 @@ int forward_impl(const lgr_view* v, int P, int M, const float* means3D, const fl
         }
         if (((uintptr_t)raw->features_rest & 15) || ((uintptr_t)raw->features_dc & 15)) {
             g_last_error = "lgr_forward_raw: features_dc / features_rest must be 16-byte aligned";
+            return LGR_ERR_INVALID_ARG;
+        }
+        if (!raw_rest_stride_ok(raw, M)) {
+            g_last_error = "lgr_forward_raw: features_rest_row_stride must be 0 (dense) or in [(M-1)*3, 256]";
             return LGR_ERR_INVALID_ARG;
         }
     }
@@ -1026,7 +1038,8 @@ int forward_impl(const lgr_view* v, int P, int M, const float* means3D, const fl
             ra.xyz = raw->xyz; ra.dc = raw->features_dc; ra.rest = raw->features_rest; ra.scaling = raw->scaling;
             ra.rotation = raw->rotation; ra.opacity = raw->opacity; ra.view = a.view; ra.proj = a.proj; ra.campos = a.campos;
             ra.prefiltered = a.prefiltered;
-            const size_t smem = raw_smem_bytes(M);
+            ra.rest_stride = raw_rest_stride(raw, M);
+            const size_t smem = raw_smem_bytes_stride(ra.rest_stride);
             LGR_CUDA_TRY(cudaFuncSetAttribute(preprocess_raw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             ProfScope ps(ST_PREPROCESS, stream);
             preprocess_raw_kernel<<<blocks, 256, smem, stream>>>(ra, radii, geo);
@@ -1357,6 +1370,11 @@ int lgr_backward_raw_end_range(const lgr_view* v, int P, int M, const lgr_raw_pa
     a.d_xyz = grads->xyz; a.d_dc = grads->features_dc; a.d_rest = grads->features_rest; a.d_scaling = grads->scaling;
     a.d_rotation = grads->rotation; a.d_opacity = grads->opacity; a.dL_dmeans2D = dL_dmeans2D;
     a.d_rgb = grads->rgb;
+    if (!raw_rest_stride_ok(params, M)) {
+        g_last_error = "lgr_backward_raw: features_rest_row_stride must be 0 (dense) or in [(M-1)*3, 256]";
+        return LGR_ERR_INVALID_ARG;
+    }
+    a.rest_stride = raw_rest_stride(params, M);
     a.block0 = first / 256;
     a.P = first + count;                       // the kernel's bound check: blocks of this launch never run past the range
     if (compact) { a.d_rest = nullptr; a.d_dc = nullptr; }
@@ -1427,6 +1445,11 @@ int lgr_backward_raw_sparse_pack(const lgr_view* v, int P, int M, const lgr_raw_
     a.view = v->viewmatrix; a.proj = v->projmatrix; a.campos = v->campos;
     a.radii = radii; a.clamped = geo.clamped; a.acc = geo.grad_acc;
     a.dL_dmeans2D = dL_dmeans2D;
+    if (!raw_rest_stride_ok(params, M)) {
+        g_last_error = "lgr_backward_raw_sparse_pack: features_rest_row_stride must be 0 (dense) or in [(M-1)*3, 256]";
+        return LGR_ERR_INVALID_ARG;
+    }
+    a.rest_stride = raw_rest_stride(params, M);
     {
         ProfScope ps(ST_SPARSE_PACK, stream);
         LGR_CUDA_TRY(cudaMemsetAsync(dL_dmeans2D, 0, sizeof(float) * 3 * (size_t)P, stream));
@@ -1635,6 +1658,13 @@ int lgr_adamw_step(int n_tensors, const lgr_adamw_tensor* tensors, double beta1,
         const double bc1 = 1.0 - pow(beta1, a.step), bc2 = 1.0 - pow(beta2, a.step);
         t.p[k] = a.param; t.g[k] = a.grad; t.m[k] = a.exp_avg; t.v[k] = a.exp_avg_sq;
         t.n[k] = a.numel;
+        if (a.row_elems < 0 || a.row_elems > 0x7fffffffLL || (a.row_elems > 0 && (a.param_row_stride < a.row_elems || a.param_row_stride > 0x7fffffffLL ||
+                                                                                 a.numel % a.row_elems != 0))) {
+            g_last_error = "lgr_adamw_step: row-strided parameter needs row_elems dividing numel and param_row_stride >= row_elems";
+            return LGR_ERR_INVALID_ARG;
+        }
+        t.row_elems[k] = (a.row_elems > 0 && a.param_row_stride != a.row_elems) ? (int)a.row_elems : 0;
+        t.row_stride[k] = (int)a.param_row_stride;
         t.decay[k] = (float)(1.0 - a.lr * weight_decay);
         t.neg_step[k] = (float)((a.lr / bc1) * -1.0);
         t.bc2_sqrt[k] = (float)pow(bc2, 0.5);

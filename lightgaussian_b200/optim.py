@@ -16,7 +16,7 @@ import ctypes as C
 
 import torch
 
-from . import capi
+from . import capi, trace
 
 
 class FusedAdamW(torch.optim.AdamW):
@@ -36,6 +36,7 @@ class FusedAdamW(torch.optim.AdamW):
             with torch.enable_grad():
                 loss = closure()
         lib = capi.load()
+        trace.bump("adamw_steps")
         by_cfg = {}
         for group in self.param_groups:
             if isinstance(group["lr"], torch.Tensor):
@@ -46,12 +47,22 @@ class FusedAdamW(torch.optim.AdamW):
                     continue
                 if p.grad.is_sparse:
                     raise RuntimeError("AdamW does not support sparse gradients")
-                if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous()):
-                    raise RuntimeError("FusedAdamW needs contiguous float32 CUDA parameters: there is no CPU path")
+                if not (p.is_cuda and p.dtype == torch.float32):
+                    raise RuntimeError("FusedAdamW needs float32 CUDA parameters: there is no CPU path")
+                # a parameter is updated IN PLACE whatever its layout: dense ones by the vectorised path, row-strided views such as
+                # the distillation student's _features_rest[:, :8, :] (scene/gaussian_model.py:129-136; registered as is by
+                # distill_train.py:79) through (row_elems, row_stride); the keys of optimizer.state stay the caller's tensors
+                row_elems = row_stride = 0
+                if not p.is_contiguous():
+                    trace.bump("adamw_strided_params")
+                    row_elems, row_stride = _row_strided(p)
+                    if row_elems == 0:
+                        raise RuntimeError(f"FusedAdamW: parameter of shape {tuple(p.shape)} and strides {p.stride()} is neither dense "
+                                           "nor a row-strided view of a dense tensor")
                 state = self.state[p]
                 if len(state) == 0:                                   # torch/optim/adam.py _init_group
                     state["step"] = torch.tensor(0.0, dtype=torch.float32)
-                    state["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                    state["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)      # dense for a non-dense view
                     state["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                 state["step"] += 1
                 g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
@@ -59,18 +70,33 @@ class FusedAdamW(torch.optim.AdamW):
                 if not (m.is_contiguous() and v.is_contiguous()):
                     raise RuntimeError("FusedAdamW: optimizer state must be contiguous")
                 key = (p.device, float(beta1), float(beta2), float(group["eps"]), float(group["weight_decay"]))
-                by_cfg.setdefault(key, []).append((p, g, m, v, float(group["lr"]), float(state["step"])))
+                by_cfg.setdefault(key, []).append((p, g, m, v, float(group["lr"]), float(state["step"]), row_elems, row_stride))
         for (device, beta1, beta2, eps, wd), items in by_cfg.items():
             for i0 in range(0, len(items), 8):
                 chunk = items[i0:i0 + 8]
                 arr = (capi.LgrAdamwTensor * len(chunk))()
-                for a, (p, g, m, v, lr, step) in zip(arr, chunk):
+                for a, (p, g, m, v, lr, step, row_elems, row_stride) in zip(arr, chunk):
                     a.param, a.grad, a.exp_avg, a.exp_avg_sq = p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr()
                     a.numel, a.lr, a.step = p.numel(), lr, step
+                    a.row_elems, a.param_row_stride = row_elems, row_stride
                 with torch.cuda.device(device):
                     st = lib.lgr_adamw_step(len(chunk), arr, beta1, beta2, eps, wd, capi.current_stream_ptr(device))
                 capi.check(st, "lgr_adamw_step")
         return loss
+
+
+def _row_strided(p):
+    """(elements per row, row stride) when `p` is a view whose rows are dense and start `stride` elements apart, else (0, 0)."""
+    if p.dim() < 2 or p.numel() == 0:
+        return 0, 0
+    inner = 1
+    for d in range(p.dim() - 1, 0, -1):          # dims 1.. must be dense among themselves
+        if p.size(d) != 1 and p.stride(d) != inner:
+            return 0, 0
+        inner *= p.size(d)
+    if p.stride(0) < inner:
+        return 0, 0
+    return inner, p.stride(0)
 
 
 def compact_rows(tensors, keep):

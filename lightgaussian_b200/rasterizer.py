@@ -208,6 +208,13 @@ class _RasterizeGaussians(torch.autograd.Function):
         # gradients of absent inputs (empty tensors) must have the inputs' (empty) shape
         def fit(g, ref):
             return g if ref.numel() != 0 else None
+        if _exchange["world"] > 1:
+            # view-parallel training that left the fused node (override_color, convert_SHs_python / compute_cov3D_python, LGR_FUSED=0,
+            # a leaf layout the fused kernels cannot read): the replicas must still step on the SUM over all ranks' views, so the
+            # per-Gaussian gradients are all-reduced here (dense NCCL: correct, but ~2x slower than the fused sparse exchange).
+            # grad_means2D stays local: it feeds per-view densification statistics, not a parameter.
+            _allreduce_unfused([grad_means3D, fit(grad_sh, sh), fit(grad_colors_precomp, colors_precomp), grad_opacities,
+                                fit(grad_scales, scales), fit(grad_rotations, rotations), fit(grad_cov3Ds_precomp, cov3Ds_precomp)])
         return (grad_means3D, grad_means2D, fit(grad_sh, sh), fit(grad_colors_precomp, colors_precomp), grad_opacities,
                 fit(grad_scales, scales), fit(grad_rotations, rotations), fit(grad_cov3Ds_precomp, cov3Ds_precomp), None)
 
@@ -264,8 +271,30 @@ class GaussianRasterizer(nn.Module):
 # Fused-activation path: the rasterizer consumes GaussianModel's six raw leaves.
 # Only gaussian_renderer.render()/count_render() use it; the reference-compatible API above is unchanged.
 # ------------------------------------------------------------------------------------------------------------------
+def rest_row_stride(rest) -> int:
+    """Row stride (floats) of a features_rest leaf the kernels can read in place, or 0 when it has to be copied.
+    Dense [P,K,3] tensors, and row-strided views of them -- the distillation student's `_features_rest[:, :8, :]`
+    (scene/gaussian_model.py:129-136: stride (45,3,1)) -- qualify: rows start at multiples of the stride, inner layout dense."""
+    if rest.dim() != 3 or rest.size(2) != 3:
+        return 0
+    if rest.is_contiguous():
+        return rest.size(1) * 3
+    P, K = rest.size(0), rest.size(1)
+    if P == 0 or K == 0:
+        return 0
+    st = rest.stride()
+    if st[2] != 1 or st[1] != 3 or st[0] < 3 * K or st[0] > 256:
+        return 0
+    # whole rows of `stride` floats are staged: the storage must extend that far behind the last row's start
+    if rest.storage_offset() + P * st[0] > rest.untyped_storage().nbytes() // 4 or rest.data_ptr() % 16:
+        return 0
+    return st[0]
+
+
 def _raw_struct(xyz, dc, rest, scaling, rotation, opacity):
-    return capi.LgrRawParams(capi.ptr(xyz), capi.ptr(dc), capi.ptr(rest), capi.ptr(scaling), capi.ptr(rotation), capi.ptr(opacity))
+    dense = rest.numel() == 0 or rest.is_contiguous()
+    return capi.LgrRawParams(capi.ptr(xyz), capi.ptr(dc), capi.ptr(rest), capi.ptr(scaling), capi.ptr(rotation), capi.ptr(opacity),
+                             0 if dense else rest_row_stride(rest))
 
 
 def _forward_raw_native(count_mode, rs, xyz, dc, rest, scaling, rotation, opacity):
@@ -274,7 +303,12 @@ def _forward_raw_native(count_mode, rs, xyz, dc, rest, scaling, rotation, opacit
     P, H, W = xyz.size(0), int(rs.image_height), int(rs.image_width)
     M = 1 + rest.size(1)
     leaves = [_f32c(t, n) if t.numel() else t for t, n in
-              ((xyz, "xyz"), (dc, "features_dc"), (rest, "features_rest"), (scaling, "scaling"), (rotation, "rotation"), (opacity, "opacity"))]
+              ((xyz, "xyz"), (dc, "features_dc"), (scaling, "scaling"), (rotation, "rotation"), (opacity, "opacity"))]
+    if rest.numel() and not rest.is_contiguous() and rest_row_stride(rest) and rest.dtype == torch.float32 and rest.is_cuda:
+        rest_c = rest                      # row-strided view: read in place through features_rest_row_stride
+    else:
+        rest_c = _f32c(rest, "features_rest") if rest.numel() else rest
+    leaves.insert(2, rest_c)
     out_color = torch.empty((3, H, W), dtype=torch.float32, device=device)
     radii = torch.empty((P,), dtype=torch.int32, device=device)
     count = score = None
@@ -307,11 +341,34 @@ def _forward_raw_native(count_mode, rs, xyz, dc, rest, scaling, rotation, opacit
 # are already SUMMED over all ranks' views: the dense leaves (xyz, scaling, rotation, opacity: 44 B/Gaussian) go through one
 # all-reduce, while the SH gradient (12*M B/Gaussian) is exchanged as its rank-1 factor dRGB (12 B/Gaussian, all-gather) and
 # rebuilt locally by lgr_sh_grad_from_views -- ~4x less NVLink traffic than all-reducing the dense gradient at degree 3.
-_exchange = {"world": 1, "group": None}
+_exchange = {"world": 1, "group": None, "warned_unfused": False, "unfused_calls": 0}
 
 
 def enable_gradient_exchange(world: int, group=None):
+    """From now on every rasterizer backward in this process returns per-Gaussian gradients SUMMED over the `world` ranks' views:
+    the fused node (`render()` on GaussianModel leaves) through the sparse NVLink peer-memory exchange, every other path through a
+    dense NCCL all-reduce inside `_RasterizeGaussians.backward` -- no path is left that silently keeps rank-local gradients."""
     _exchange["world"], _exchange["group"] = int(world), group
+
+
+def unfused_exchange_calls() -> int:
+    """how many backward passes took the dense all-reduce of the unfused node since start (bench.py / tests: should be 0 on the hot path)"""
+    return _exchange["unfused_calls"]
+
+
+def _allreduce_unfused(grads):
+    import torch.distributed as dist
+    import warnings
+    if not _exchange["warned_unfused"]:
+        _exchange["warned_unfused"] = True
+        warnings.warn("lightgaussian_b200: view-parallel backward outside the fused render() node -- gradients are summed with a dense "
+                      "NCCL all-reduce (correct, slower than the sparse peer-memory exchange of the fused path)", stacklevel=3)
+    _exchange["unfused_calls"] += 1
+    from . import trace
+    trace.bump("unfused_exchange")
+    hs = [dist.all_reduce(g, op=dist.ReduceOp.SUM, group=_exchange["group"], async_op=True) for g in grads if g is not None and g.numel()]
+    for h in hs:
+        h.wait()
 
 
 def _raw_grads_struct(xyz, dc, rest, scaling, rotation, opacity, rgb=None):
@@ -377,8 +434,11 @@ class _SymmExchange:
     def __init__(self, device, P, world, group):
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm_mem
+        if world > 8:
+            raise RuntimeError("peer-memory all-reduce supports at most 8 ranks (one NVSwitch domain)")
         grp = group if group is not None else dist.group.WORLD
         self.group_name = grp.group_name
+        self.capacity = P
         self.n = (P * 11 + 1023) // 1024 * 1024
         self.bufs = [symm_mem.empty(self.n, dtype=torch.float32, device=device) for _ in range(2)]
         self.hdls = [symm_mem.rendezvous(b, self.group_name) for b in self.bufs]
@@ -422,8 +482,14 @@ def _symm_exchange(device, P, world, group):
     """collectively agreed: either every rank gets symmetric buffers or none does (then NCCL is used)"""
     import os
     import torch.distributed as dist
-    key = (str(device), P, world)
-    if key not in _symm_cache:
+    # ONE exchange object per (device, world): P changes at every prune / densify event, and keying the cache by P pinned a fresh
+    # pair of peer-mapped buffers per value for the life of the process.  The flat buffer is laid out from the call's P, so it is
+    # reused exactly while P stays the same and replaced (the old one dropped) when P changes; every rank sees the same P.
+    key = (str(device), world)
+    cur = _symm_cache.get(key, "none")
+    if cur == "none" or (cur is not None and cur.capacity != P):
+        _symm_cache.pop(key, None)
+        del cur
         xb, ok = None, 1
         # Measured on 2 and 4 B200s (DESIGN.md section 6): NCCL's all-reduce is as fast or faster than our peer-memory and
         # NVLS multimem kernels for this 132 MB payload once the rebuild kernel competes for HBM, so NCCL is the default;
@@ -450,7 +516,10 @@ class _SparseExchange:
 
     def __init__(self, device, P, world, group):
         lib = capi.load()
+        if world > 8:
+            raise RuntimeError("the sparse peer-memory exchange supports at most 8 ranks (one NVSwitch domain)")
         self.world = world
+        self.capacity = P          # the layout inside the buffers is computed from each call's P <= capacity
         n = (int(lib.lgr_sparse_exchange_bytes(P)) + 3) // 4
         self.ws = torch.empty(int(lib.lgr_sparse_workspace_bytes(P)), dtype=torch.uint8, device=device)
         if world > 1:
@@ -483,14 +552,22 @@ _sparse_cache = {}
 def _sparse_exchange(device, P, world, group):
     """collectively agreed: either every rank gets the peer-mapped buffers or none does (then the dense NCCL exchange is used).
     LGR_EXCHANGE=dense selects the dense exchange explicitly."""
-    key = (str(device), P, world)
-    if key not in _sparse_cache:
+    # ONE exchange object per (device, world), sized for a capacity >= P (kernels lay the buffer out from the call's P): P shrinks at
+    # every prune event and may grow when densifying; only growth beyond the capacity re-allocates (x1.25, the old buffers are
+    # dropped first), so a training run no longer pins a new pair of peer-mapped buffers per distinct P.
+    key = (str(device), world)
+    cur = _sparse_cache.get(key, "none")
+    if cur == "none" or (cur is not None and cur.capacity < P):
+        grow = cur != "none" and cur is not None
+        _sparse_cache.pop(key, None)
+        del cur
+        cap = int(P * 1.25) if grow else P
         xs, ok = None, 1
         if _os.environ.get("LGR_EXCHANGE", "sparse") != "sparse":
             ok = 0
         else:
             try:
-                xs = _SparseExchange(device, P, world, group)
+                xs = _SparseExchange(device, cap, world, group)
             except Exception as ex:  # noqa: BLE001  (no P2P / API drift: the NCCL path still works)
                 print(f"lightgaussian_b200: sparse peer-memory exchange unavailable ({type(ex).__name__}: {ex}); using the dense NCCL exchange", flush=True)
                 ok = 0
@@ -507,7 +584,7 @@ def exchange_info(world):
     """("sparse-p2p" | "dense-nccl" | "none", rows published by this rank in its last backward or None) -- diagnostics for bench.py"""
     if world <= 1:
         return "none", None
-    for (dev, P, w), xs in _sparse_cache.items():
+    for (dev, w), xs in _sparse_cache.items():
         if w == world and xs is not None:
             rows = int(xs.bufs[xs.turn][3:4].view(torch.int32).item())
             return "sparse-p2p", rows
@@ -523,7 +600,7 @@ def _backward_raw_sparse(xs, rs, num_rendered, grad_out_color, xyz, dc, rest, sc
     P, M = xyz.size(0), 1 + rest.size(1)
     H, W = grad_out_color.size(1), grad_out_color.size(2)
     g2d = torch.empty((P, 3), dtype=torch.float32, device=device)
-    g = [torch.empty_like(t) for t in (xyz, dc, rest, scaling, rotation, opacity)]
+    g = [torch.empty(t.shape, dtype=torch.float32, device=device) for t in (xyz, dc, rest, scaling, rotation, opacity)]
     dpix = _f32c(grad_out_color, "grad_out_color")
     main = torch.cuda.current_stream(device)
     k = xs.next()
@@ -584,7 +661,7 @@ def _backward_raw_exchange(rs, num_rendered, grad_out_color, xyz, dc, rest, scal
     d_rgb = torch.empty((P, 3), dtype=torch.float32, device=device)
     all_rgb = torch.empty((world, P, 3), dtype=torch.float32, device=device)
     all_cam = torch.empty((world, 3), dtype=torch.float32, device=device)
-    d_dc, d_rest = torch.empty_like(dc), torch.empty_like(rest)
+    d_dc, d_rest = torch.empty(dc.shape, dtype=torch.float32, device=device), torch.empty(rest.shape, dtype=torch.float32, device=device)
     dpix = _f32c(grad_out_color, "grad_out_color")
     main = torch.cuda.current_stream(device)
     side = _side_streams.setdefault(str(device), torch.cuda.Stream(device=device))
@@ -663,7 +740,7 @@ def backward_raw_native(rs, num_rendered, grad_out_color, xyz, dc, rest, scaling
         d_rgb = torch.empty((P, 3), dtype=torch.float32, device=device)
         g = [g_xyz, None, None, g_scal, g_rot, g_op]
     else:
-        g = [torch.empty_like(t) for t in (xyz, dc, rest, scaling, rotation, opacity)]
+        g = [torch.empty(t.shape, dtype=torch.float32, device=device) for t in (xyz, dc, rest, scaling, rotation, opacity)]
     if P != 0:
         dpix = _f32c(grad_out_color, "grad_out_color")
         with torch.cuda.device(device):

@@ -16,7 +16,10 @@ import os
 
 import torch.nn.functional as F
 
-from .rasterizer import (GaussianRasterizationSettings, GaussianRasterizer, rasterize_raw_leaves, fused_activations_match_torch)
+from . import trace
+
+from .rasterizer import (GaussianRasterizationSettings, GaussianRasterizer, rasterize_raw_leaves, fused_activations_match_torch,
+                         rest_row_stride)
 
 _LEAVES = ("_xyz", "_features_dc", "_features_rest", "_scaling", "_rotation", "_opacity")
 
@@ -37,9 +40,14 @@ def _can_fuse(pc, pipe, override_color) -> bool:
     if getattr(pc, "rotation_activation", F.normalize) is not F.normalize:
         return False
     t = pc._xyz
-    if not (t.is_cuda and all(getattr(pc, n).dtype == torch.float32 and getattr(pc, n).is_contiguous() for n in _LEAVES)):
+    # every leaf dense, except that _features_rest may be a row-strided view: the distillation student's
+    # `_features_rest[:, :8, :]` (scene/gaussian_model.py:129-136) is read in place through its row stride
+    if not (t.is_cuda and all(getattr(pc, n).dtype == torch.float32 and (getattr(pc, n).is_contiguous() or n == "_features_rest")
+                              for n in _LEAVES)):
         return False
     if pc._features_rest.dim() != 3 or pc._features_dc.shape[1] != 1 or pc._features_rest.shape[1] < 1:
+        return False
+    if not pc._features_rest.is_contiguous() and rest_row_stride(pc._features_rest) == 0:
         return False
     if (pc.active_sh_degree + 1) ** 2 > 1 + pc._features_rest.shape[1]:
         return False
@@ -96,10 +104,14 @@ def _render(viewpoint_camera, pc, pipe, bg_color, scaling_modifier, override_col
         f_count=f_count,
     )
     if _can_fuse(pc, pipe, override_color):
+        trace.bump("render_fused")
+        if not pc._features_rest.is_contiguous():
+            trace.bump("render_fused_strided_rest")
         outputs = rasterize_raw_leaves(pc._xyz, screenspace_points, pc._features_dc, pc._features_rest, pc._scaling, pc._rotation,
                                        pc._opacity, settings)
         return _package(outputs, screenspace_points, f_count)
 
+    trace.bump("render_unfused")
     rasterizer = GaussianRasterizer(raster_settings=settings)
 
     geometry = dict(scales=None, rotations=None, cov3D_precomp=None)

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/lgrast.h but not exported"
     lib.lgr_abi_version.restype = C.c_int
-    assert lib.lgr_abi_version() == 1
+    assert lib.lgr_abi_version() == 2
 
 
 def test_layout_queries_need_no_gpu():

@@ -6,7 +6,7 @@ import torch
 
 from lightgaussian_b200.synth import make_scene, make_cameras
 from tests import util
-from tests.util import run_ours, run_ref, rel_inf, rel_l2, view_from_camera
+from tests.util import run_ours, run_ref, rel_inf, rel_l2, view_from_camera, assert_elementwise
 
 pytestmark = pytest.mark.gpu
 
@@ -75,6 +75,7 @@ def test_full_size_parity_with_reference_kernels(big):
         a, b = ours["grads"][k], ref["grads"][k].reshape(ours["grads"][k].shape)
         assert rel_inf(a, b) <= 1e-3, f"{k}: rel_inf {rel_inf(a, b)}"
         assert rel_l2(a, b) <= 1e-3, f"{k}: rel_l2 {rel_l2(a, b)}"
+        assert_elementwise(a, b, k)
     cnt = run_ours(view, act, count=True)
     refc = run_ref(view, act, count=True)
     assert np.all(refc["gaussians_count"] <= cnt["gaussians_count"])   # the reference's racy counter only loses updates
@@ -86,3 +87,23 @@ def test_full_size_parity_with_reference_kernels(big):
     rho = np.corrcoef(ra, rb)[0, 1]
     print(f"reference racy counter loses {100 * lost:.1f} % of the updates; Spearman rho(exact score, racy score) = {rho:.3f}")
     assert 0.0 <= lost < 1.0 and np.isfinite(rho)
+
+
+@pytest.mark.skipif(not util.have_ref(), reason="oracle/_ref/libref_rasterizer.so not built (needs /root/reference)")
+def test_bench_config_3m_1080p_parity_with_reference_kernels():
+    """The exact bench.py workload (BASELINE.json configs[2] scene: 3M Gaussians, SH degree 3, 1920x1080, camera 0 of the bench's
+    16): forward bit-identical to the reference's kernels, gradients to 1e-3."""
+    scene = make_scene(3_000_000, sh_degree=3, seed=0)
+    view = view_from_camera(make_cameras(16, W, H)[0], (0.0, 0.0, 0.0), 3, 1.0)
+    dpix = np.random.default_rng(11).standard_normal((3, H, W)).astype(np.float32)
+    ours = run_ours(view, scene["act"], dL_dpix=dpix)
+    ref = run_ref(view, scene["act"], dL_dpix=dpix)
+    assert ours["num_rendered"] == ref["num_rendered"]
+    np.testing.assert_array_equal(ours["radii"], ref["radii"])
+    np.testing.assert_array_equal(ours["color"], ref["color"])
+    np.testing.assert_array_equal(ours["final_T"], ref["final_T"])
+    for k in ("dL_dmeans2D", "dL_dcolors", "dL_dopacity", "dL_dmeans3D", "dL_dcov3D", "dL_dsh", "dL_dscales", "dL_drotations"):
+        a, b = ours["grads"][k], ref["grads"][k].reshape(ours["grads"][k].shape)
+        assert rel_inf(a, b) <= 1e-3, f"{k}: rel_inf {rel_inf(a, b)}"
+        assert rel_l2(a, b) <= 1e-3, f"{k}: rel_l2 {rel_l2(a, b)}"
+        assert_elementwise(a, b, k)

@@ -117,3 +117,48 @@ def test_compact_sh_gradient_rebuild_matches_dense():
     assert np.abs(ref_rest).max() > 0
     assert rel_inf(d_rest.cpu().numpy(), ref_rest) <= 1e-3 and rel_l2(d_rest.cpu().numpy(), ref_rest) <= 1e-4
     assert rel_inf(d_dc.cpu().numpy(), ref_dc) <= 1e-3
+
+
+def _student_like(raw, device="cuda"):
+    """GaussianParams whose _features_rest is exactly what GaussianModel.onedownSHdegree() leaves behind for 3 -> 2
+    (scene/gaussian_model.py:129-136): a NON-contiguous [P,8,3] view (strides 45,3,1) of a detached [P,15,3] clone, requires_grad."""
+    pc = GaussianParams(raw, 3, device)
+    full = pc._features_rest.clone().detach()
+    pc._features_rest = full[:, :8, :]
+    pc._features_rest.requires_grad = True
+    pc.max_sh_degree, pc.active_sh_degree = 2, 2
+    return pc
+
+
+@pytest.mark.parametrize("P", [3000 + 5, 4096, 33])
+def test_strided_student_features_rest_takes_the_fused_path(P):
+    """The distillation student's leaf is read in place through its row stride: same image bit for bit and same gradients as a
+    contiguous copy of the same values; the gradient comes back dense [P,8,3]."""
+    from lightgaussian_b200 import renderer, trace
+    W, H = 128, 96
+    scene = make_scene(P, sh_degree=3, seed=200 + P, scale_mult=1.5)
+    cam = TorchCamera(make_cameras(5, W, H)[2], "cuda")
+    bg = torch.tensor([0.1, 0.3, 0.5], device="cuda")
+    pipe = pipeline_params()
+    tgt = torch.rand(3, H, W, generator=torch.Generator().manual_seed(5)).cuda()
+    stu = _student_like(scene["raw"])
+    assert not stu._features_rest.is_contiguous() and stu._features_rest.stride() == (45, 3, 1)
+    assert renderer._can_fuse(stu, pipe, None)
+    n0 = trace.counters.get("render_fused_strided_rest", 0)
+    pkg = renderer.render(cam, stu, pipe, bg)
+    assert trace.counters.get("render_fused_strided_rest", 0) == n0 + 1
+    ((pkg["render"] - tgt) ** 2).mean().backward()
+    raw2 = dict(scene["raw"])
+    raw2["features_rest"] = np.ascontiguousarray(raw2["features_rest"][:, :8])
+    con = GaussianParams(raw2, 2, "cuda")
+    pkg2 = renderer.render(cam, con, pipe, bg)
+    ((pkg2["render"] - tgt) ** 2).mean().backward()
+    assert torch.equal(pkg["render"], pkg2["render"]) and torch.equal(pkg["radii"], pkg2["radii"])
+    g = stu._features_rest.grad
+    assert g.shape == (P, 8, 3) and g.is_contiguous()
+    for a, b, name in zip(stu.parameters(), con.parameters(), ("xyz", "dc", "rest", "scaling", "rotation", "opacity")):
+        assert rel_inf(a.grad.cpu().numpy(), b.grad.cpu().numpy()) <= 1e-3, name
+    # count mode on the strided leaf
+    c1 = renderer.count_render(cam, stu, pipe, bg)
+    c2 = renderer.count_render(cam, con, pipe, bg)
+    assert torch.equal(c1["gaussians_count"], c2["gaussians_count"]) and torch.equal(c1["render"], c2["render"])

@@ -250,3 +250,33 @@ def test_full_size_3m_step_matches_torch():
         ob.step()
     assert torch.equal(pa, pb)
     assert torch.equal(oa.state[pa]["exp_avg_sq"], ob.state[pb]["exp_avg_sq"])
+
+
+def test_row_strided_parameter_is_updated_in_place_bit_exactly():
+    """distill_train.py:79-80 registers the student's NON-contiguous _features_rest[:, :8, :] (scene/gaussian_model.py:129-136) in the
+    optimizer.  FusedAdamW must update that view in place (the caller's tensor stays the key of optimizer.state) with the same bits as
+    torch.optim.AdamW on a contiguous copy, leaving the columns outside the view untouched."""
+    import torch
+    from lightgaussian_b200.optim import FusedAdamW
+    P = 5000 + 3
+    g = torch.Generator().manual_seed(0)
+    full0 = torch.randn(P, 15, 3, generator=g).cuda()
+    full = full0.clone()
+    view = full[:, :8, :]
+    view.requires_grad = True
+    assert not view.is_contiguous()
+    ref = view.detach().clone().contiguous().requires_grad_(True)
+    lr = 2.5e-3 / 20
+    opt = FusedAdamW([{"params": [view], "lr": lr, "name": "f_rest"}], lr=0.0, eps=1e-15)
+    opt_ref = torch.optim.AdamW([{"params": [ref], "lr": lr, "name": "f_rest"}], lr=0.0, eps=1e-15)
+    for step in range(12):
+        grad = (torch.randn(P, 8, 3, generator=g) * 10.0 ** float(torch.randint(-6, 1, (1,), generator=g))).cuda()
+        grad[::7] = 0.0
+        view.grad, ref.grad = grad.clone(), grad.clone()
+        opt.step()
+        opt_ref.step()
+    assert torch.equal(view.detach(), ref.detach())
+    st, st_ref = opt.state[view], opt_ref.state[ref]
+    assert st["exp_avg"].is_contiguous() and torch.equal(st["exp_avg"], st_ref["exp_avg"]) and torch.equal(st["exp_avg_sq"], st_ref["exp_avg_sq"])
+    assert torch.equal(full[:, 8:, :], full0[:, 8:, :])                 # coefficients outside the view are untouched
+    assert view.data_ptr() == full.data_ptr()                           # updated in place, no re-materialisation

@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 from tests import util
-from tests.util import CONFIGS, make_config, run_ours, run_ref, rel_inf, rel_l2, oracle_from_geometry
+from tests.util import CONFIGS, make_config, run_ours, run_ref, rel_inf, rel_l2, oracle_from_geometry, assert_elementwise
 from oracle.lgo import Oracle
 
 pytestmark = pytest.mark.gpu
@@ -108,6 +108,7 @@ def test_backward_vs_oracle(name):
         assert np.isfinite(a).all(), k
         assert rel_inf(a, b) <= GRAD_TOL, f"{k}: rel_inf {rel_inf(a, b)}"
         assert rel_l2(a, b) <= GRAD_TOL, f"{k}: rel_l2 {rel_l2(a, b)}"
+        assert_elementwise(a, b, k)
     # culled Gaussians get exact zeros in every output
     cul = ours["radii"] <= 0
     for k in mine:
@@ -176,6 +177,58 @@ def test_backward_vs_reference_kernels(name):
         a, b = ours["grads"][k], ref["grads"][k].reshape(ours["grads"][k].shape)
         assert rel_inf(a, b) <= GRAD_TOL, f"{k}: rel_inf {rel_inf(a, b)}"
         assert rel_l2(a, b) <= GRAD_TOL, f"{k}: rel_l2 {rel_l2(a, b)}"
+        assert_elementwise(a, b, k)
+
+
+@needs_ref
+def test_precomputed_inputs_vs_reference_kernels():
+    """colors_precomp + cov3D_precomp (the convert_SHs_python / compute_cov3D_python pipeline flags) against the reference's own
+    kernels: forward bit-identical, gradients to tolerance, no SH / scale / rotation gradients."""
+    act, view, dpix = make_config("deg1")
+    o = Oracle()
+    g = o.preprocess(view, act["means3D"], act["opacities"], shs=act["shs"], scales=act["scales"], rotations=act["rotations"])
+    P = act["means3D"].shape[0]
+    colors = np.random.default_rng(5).uniform(0, 1, (P, 3)).astype(np.float32)
+    cov = g["cov3D"].copy()
+    cov[g["radii"] <= 0] = np.array([1e-4, 0, 0, 1e-4, 0, 1e-4], np.float32)
+    ours = run_ours(view, act, dL_dpix=dpix, colors_precomp=colors, cov3D_precomp=cov, tile_cull=False)
+    ref = run_ref(view, act, dL_dpix=dpix, colors_precomp=colors, cov3D_precomp=cov)
+    assert ours["num_rendered"] == ref["num_rendered"]
+    np.testing.assert_array_equal(ours["radii"], ref["radii"])
+    np.testing.assert_array_equal(ours["point_list"], ref["point_list"])
+    np.testing.assert_array_equal(ours["color"], ref["color"])
+    np.testing.assert_array_equal(ours["final_T"], ref["final_T"])
+    for k in ("dL_dmeans2D", "dL_dcolors", "dL_dopacity", "dL_dmeans3D", "dL_dcov3D"):
+        a, b = ours["grads"][k], ref["grads"][k].reshape(ours["grads"][k].shape)
+        assert rel_inf(a, b) <= GRAD_TOL, f"{k}: rel_inf {rel_inf(a, b)}"
+        assert_elementwise(a, b, k)
+
+
+@needs_ref
+@pytest.mark.parametrize("cam", ["sphere", "inside"])
+def test_config_c1_10k_400x400_vs_reference_kernels(cam):
+    """BASELINE.json configs[0] literally: 10 000 synthetic Gaussians, one 400x400 camera, forward render -- plus the correctness-only
+    camera INSIDE the cube (z <= 0.2 cull, 1.3 tanfov clamp, huge splats) of SURVEY.md section 8d, and the backward on both."""
+    from lightgaussian_b200.synth import make_scene, make_cameras, inside_camera
+    scene = make_scene(10_000, sh_degree=3, seed=0)
+    c = inside_camera(400, 400) if cam == "inside" else make_cameras(1, 400, 400)[0]
+    view = util.view_from_camera(c, (0.0, 0.0, 0.0), 3, 1.0)
+    dpix = np.random.default_rng(3).standard_normal((3, 400, 400)).astype(np.float32)
+    ours = run_ours(view, scene["act"], dL_dpix=dpix, tile_cull=False)
+    ref = run_ref(view, scene["act"], dL_dpix=dpix)
+    assert ours["num_rendered"] == ref["num_rendered"] > 0
+    np.testing.assert_array_equal(ours["radii"], ref["radii"])
+    np.testing.assert_array_equal(ours["point_list"], ref["point_list"])
+    np.testing.assert_array_equal(ours["ranges"], ref["ranges"])
+    assert np.abs(ours["color"] - ref["color"]).max() <= RGB_TOL
+    np.testing.assert_array_equal(ours["color"], ref["color"])
+    np.testing.assert_array_equal(ours["n_contrib"], ref["n_contrib"])
+    culled = run_ours(view, scene["act"])                       # the product default (exact tile culling): same image
+    np.testing.assert_array_equal(culled["color"], ref["color"])
+    for k in ("dL_dmeans2D", "dL_dcolors", "dL_dopacity", "dL_dmeans3D", "dL_dcov3D", "dL_dsh", "dL_dscales", "dL_drotations"):
+        a, b = ours["grads"][k], ref["grads"][k].reshape(ours["grads"][k].shape)
+        assert rel_inf(a, b) <= GRAD_TOL, f"{k}: rel_inf {rel_inf(a, b)}"
+        assert_elementwise(a, b, k)
 
 
 @needs_ref

@@ -237,6 +237,28 @@ def rel_inf(a, b, eps=1e-12):
     return float(np.abs(a - b).max(initial=0.0) / max(np.abs(b).max(initial=0.0), eps))
 
 
+def elem_rel(a, b, floor=1e-6):
+    """Per-element relative error |a-b|/|b| on the entries with |b| > floor (second gradient metric).
+    Returns (sorted errors, count); quantiles of it are what the tests bound -- the reference's own float atomics make single small
+    entries differ run to run, so a max over millions of entries is not a stable statistic, its quantiles are."""
+    a, b = np.asarray(a, np.float64).ravel(), np.asarray(b, np.float64).ravel()
+    m = np.abs(b) > floor
+    if not m.any():
+        return np.zeros(0), 0
+    e = np.sort(np.abs(a[m] - b[m]) / np.abs(b[m]))
+    return e, int(m.sum())
+
+
+def assert_elementwise(a, b, name, tol=1e-3, frac=0.995, median=2e-5):
+    """at least `frac` of the entries with |b| > 1e-6 agree to `tol` relative, and the median relative error is <= `median`"""
+    e, n = elem_rel(a, b)
+    if n == 0:
+        return
+    q = e[min(n - 1, int(frac * n))]
+    assert q <= tol, f"{name}: {100 * frac:.1f} % quantile of the per-element relative error is {q:.2e} (> {tol:g}; n = {n})"
+    assert e[n // 2] <= median, f"{name}: median per-element relative error {e[n // 2]:.2e} (> {median:g})"
+
+
 def rel_l2(a, b, eps=1e-30):
     a, b = np.asarray(a, np.float64).ravel(), np.asarray(b, np.float64).ravel()
     return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), eps))
