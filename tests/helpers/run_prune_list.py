@@ -18,6 +18,8 @@ parser.add_argument("--out", type=str)
 args = parser.parse_args(sys.argv[1:])
 safe_state(True)
 dataset, opt, pipe = lp.extract(args), op.extract(args), pp.extract(args)
+import os
+os.makedirs(dataset.model_path, exist_ok=True)       # prepare_output_and_logger() does this in the scripts (utils/logger_utils.py:33)
 gaussians = GaussianModel(dataset.sh_degree)
 scene = Scene(dataset, gaussians)
 gaussians.training_setup(opt)
