@@ -48,6 +48,7 @@ def parse_args():
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--cams", type=int, default=16, help="distinct synthetic cameras cycled through")
+    ap.add_argument("--blend-mode", type=int, default=0, help="DIAGNOSTIC: 0 = ring blend kernels (default), 1 = the round-1 blend kernels")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -394,6 +395,7 @@ def main():
         from lightgaussian_b200 import capi, rasterizer
         from lightgaussian_b200.renderer import render as render_fn
         capi.load()
+        capi.set_blend_mode(args.blend_mode)
         kind = None
     elif stock is not None:
         render_fn, kind = stock[0], "reference"

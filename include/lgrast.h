@@ -272,6 +272,11 @@ size_t lgr_binning_layout(int num_rendered, int width, int height, size_t* out, 
 /* Kernel launches issued by this library since load (for bench.py's gpu_launches). */
 uint64_t lgr_launch_count(void);
 
+/* Diagnostics / A-B measurements: which blend kernels forward and backward launch.  0 (default) = the shared-ring kernels
+ * (csrc/lgr_blend.cuh: producer warp + TMA-staged per-instance records), 1 = the round-1 per-warp kernels.  Process-wide; a
+ * backward must run in the mode its forward ran in (the ring backward streams the records the ring forward stored). */
+int lgr_set_blend_mode(int mode);
+
 /* Exact tile-level culling at binning time (default on): (tile, Gaussian) instances in which no pixel can reach
  * alpha >= 1/255 are not listed.  Images, gradients and significance are unchanged; only the internal lists shrink.
  * Turn it off to obtain per-tile lists identical to the reference's (tests).  num_rendered always reports the

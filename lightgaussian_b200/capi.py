@@ -238,6 +238,11 @@ def binning_layout(R: int, W: int, H: int):
     return dict(point_list=int(out[0])), int(total)
 
 
+def set_blend_mode(mode: int) -> None:
+    """0 = ring kernels (default), 1 = round-1 kernels (A/B measurements)"""
+    check(load().lgr_set_blend_mode(int(mode)), "lgr_set_blend_mode")
+
+
 def set_tile_culling(on: bool):
     """exact tile-level culling at binning time (default on); off = per-tile lists identical to the reference's"""
     check(load().lgr_set_tile_culling(int(on)), "lgr_set_tile_culling")

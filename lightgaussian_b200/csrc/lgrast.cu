@@ -43,6 +43,7 @@ constexpr int ACC_STRIDE = 12;  // floats per Gaussian in the backward accumulat
 // The per-Gaussian factors (conic, opacity, viewport) are applied once per Gaussian in K8 (accum_to_grad2d).
 
 thread_local std::string g_last_error;
+int g_blend_mode = 0;   // 0 = ring kernels (lgr_blend.cuh), 1 = round-1 kernels (kept for A/B measurements and as a cross-check in the tests)
 std::atomic<uint64_t> g_launches{0};
 
 // ---- optional per-stage device timing (CUDA events on the launch stream), used by bench.py's roofline ----
@@ -221,6 +222,7 @@ struct BinningState {
     void* keys_sorted;          // [R]
     char* cub_temp;
     size_t cub_temp_bytes;
+    float* records;             // [R][12] per-instance records in list order, written by the forward blend for the chunks it visits
     bool wide_keys;
     size_t offs[1];
     size_t total;
@@ -247,6 +249,7 @@ BinningState carve_binning(char* base, size_t R, int W, int H)
                                         (uint32_t*)nullptr, (int)Rn, 0, bits);
     b.cub_temp_bytes = bytes;
     b.cub_temp = c.take<char>(bytes);
+    b.records = c.take<float>(Rn * 12);
     b.total = align_up(c.off, 256);
     return b;
 }
@@ -918,6 +921,7 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(PreBackArgs a)
 
 }  // namespace
 #include "lgr_raw.cuh"
+#include "lgr_blend.cuh"
 #include "lgr_sparse.cuh"
 #include "lgr_loss.cuh"
 #include "lgr_optim.cuh"
@@ -1114,7 +1118,15 @@ int forward_impl(const lgr_view* v, int P, int M, const float* means3D, const fl
     {
         const int tiles = gx * gy;
         ProfScope ps(count_mode ? ST_BLEND_FWD_COUNT : ST_BLEND_FWD, stream);
-        if (count_mode)
+        if (g_blend_mode == 0 && count_mode)
+            blend_forward_ring_kernel<true, false><<<tiles, BL_THREADS, 0, stream>>>(img.ranges, bin.point_list, W, H, gx, geo.means2D, geo.conic_opacity,
+                                                                                      geo.rgb, v->background, img.final_T, img.n_contrib, out_color,
+                                                                                      gaussians_count, nullptr);
+        else if (g_blend_mode == 0)
+            blend_forward_ring_kernel<false, true><<<tiles, BL_THREADS, 0, stream>>>(img.ranges, bin.point_list, W, H, gx, geo.means2D, geo.conic_opacity,
+                                                                                      geo.rgb, v->background, img.final_T, img.n_contrib, out_color,
+                                                                                      nullptr, bin.records);
+        else if (count_mode)
             blend_forward_kernel<true><<<tiles, 256, 0, stream>>>(img.ranges, bin.point_list, W, H, gx, geo.means2D, geo.conic_opacity,
                                                                    geo.rgb, v->background, img.final_T, img.n_contrib, out_color,
                                                                    gaussians_count);
@@ -1142,6 +1154,16 @@ extern "C" {
 int lgr_abi_version(void) { return LGR_ABI_VERSION; }
 const char* lgr_last_error(void) { return g_last_error.c_str(); }
 uint64_t lgr_launch_count(void) { return g_launches.load(); }
+
+int lgr_set_blend_mode(int mode)
+{
+    if (mode != 0 && mode != 1) {
+        g_last_error = "lgr_set_blend_mode: 0 = ring kernels (default), 1 = round-1 kernels";
+        return LGR_ERR_INVALID_ARG;
+    }
+    g_blend_mode = mode;
+    return LGR_OK;
+}
 
 int lgr_set_tile_culling(int on)
 {
@@ -1256,8 +1278,13 @@ int lgr_backward(const lgr_view* v, int P, int M, int num_rendered, const float*
     }
     if (num_rendered > 0) {
         ProfScope ps(ST_BLEND_BWD, stream);
-        blend_backward_kernel<<<gx * gy, 256, 0, stream>>>(img.ranges, bin.point_list, W, H, gx, geo.means2D, geo.conic_opacity, geo.rgb,
-                                                            v->background, img.final_T, img.n_contrib, dL_dout_color, geo.grad_acc);
+        if (g_blend_mode == 0) {
+            LGR_CUDA_TRY(cudaFuncSetAttribute(blend_backward_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blend_back_smem_bytes()));
+            blend_backward_ring_kernel<<<gx * gy, BL_THREADS, blend_back_smem_bytes(), stream>>>(img.ranges, bin.records, W, H, gx, v->background, img.final_T,
+                                                                                                   img.n_contrib, dL_dout_color, geo.grad_acc);
+        } else
+            blend_backward_kernel<<<gx * gy, 256, 0, stream>>>(img.ranges, bin.point_list, W, H, gx, geo.means2D, geo.conic_opacity, geo.rgb,
+                                                                v->background, img.final_T, img.n_contrib, dL_dout_color, geo.grad_acc);
         LGR_LAUNCH_CHECK("blend_backward_kernel", debug, stream);
     }
     PreBackArgs a;
@@ -1315,8 +1342,13 @@ int lgr_backward_raw_begin(const lgr_view* v, int P, int num_rendered, const int
     }
     if (num_rendered > 0) {
         ProfScope ps(ST_BLEND_BWD, stream);
-        blend_backward_kernel<<<gx * gy, 256, 0, stream>>>(img.ranges, bin.point_list, W, H, gx, geo.means2D, geo.conic_opacity, geo.rgb,
-                                                            v->background, img.final_T, img.n_contrib, dL_dout_color, geo.grad_acc);
+        if (g_blend_mode == 0) {
+            LGR_CUDA_TRY(cudaFuncSetAttribute(blend_backward_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blend_back_smem_bytes()));
+            blend_backward_ring_kernel<<<gx * gy, BL_THREADS, blend_back_smem_bytes(), stream>>>(img.ranges, bin.records, W, H, gx, v->background, img.final_T,
+                                                                                                   img.n_contrib, dL_dout_color, geo.grad_acc);
+        } else
+            blend_backward_kernel<<<gx * gy, 256, 0, stream>>>(img.ranges, bin.point_list, W, H, gx, geo.means2D, geo.conic_opacity, geo.rgb,
+                                                                v->background, img.final_T, img.n_contrib, dL_dout_color, geo.grad_acc);
         LGR_LAUNCH_CHECK("blend_backward_kernel", debug, stream);
     }
     if (d_rgb) {

@@ -272,6 +272,23 @@ def test_tile_culling_changes_lists_but_not_results(name):
         assert cull["num_listed"] < full["num_listed"]
 
 
+@pytest.mark.parametrize("name", list(CONFIGS))
+def test_ring_kernels_equal_the_round1_kernels(name):
+    """The shared-ring blend kernels (producer warp, TMA-staged records, sign-of-T termination, two-scalar backward reduction) against
+    the round-1 per-warp kernels of the same library: forward outputs and significance counts bit-identical, gradients to tolerance."""
+    act, view, dpix = make_config(name)
+    new = run_ours(view, act, count=True)
+    old = run_ours(view, act, count=True, blend_mode=1)
+    for k in ("color", "final_T", "n_contrib", "gaussians_count", "important_score", "radii"):
+        np.testing.assert_array_equal(new[k], old[k], err_msg=k)
+    gn = run_ours(view, act, dL_dpix=dpix)
+    go = run_ours(view, act, dL_dpix=dpix, blend_mode=1)
+    np.testing.assert_array_equal(gn["color"], go["color"])
+    for k in gn["grads"]:
+        assert rel_inf(gn["grads"][k], go["grads"][k]) <= GRAD_TOL, f"{k}: {rel_inf(gn['grads'][k], go['grads'][k])}"
+        assert_elementwise(gn["grads"][k], go["grads"][k], k)
+
+
 # ------------------------------------------------------------------------------------------------
 # edge cases (empty / ragged / degenerate inputs)
 # ------------------------------------------------------------------------------------------------

@@ -51,7 +51,8 @@ def _empty():
     return torch.Tensor([])
 
 
-def run_ours(view: View, act: dict, count=False, dL_dpix=None, colors_precomp=None, cov3D_precomp=None, debug=False, tile_cull=True):
+def run_ours(view: View, act: dict, count=False, dL_dpix=None, colors_precomp=None, cov3D_precomp=None, debug=False, tile_cull=True,
+             blend_mode=0):
     """tile_cull=False makes the per-tile lists identical to the reference's (needed to compare point_list / ranges /
     n_contrib); the product default (True) lists only instances that can contribute."""
     import torch
@@ -59,10 +60,12 @@ def run_ours(view: View, act: dict, count=False, dL_dpix=None, colors_precomp=No
     from lightgaussian_b200.rasterizer import _C
     dev = "cuda"
     capi.set_tile_culling(tile_cull)
+    capi.set_blend_mode(blend_mode)      # 0 = ring kernels (the product default), 1 = the round-1 kernels
     try:
         return _run_ours(view, act, count, dL_dpix, colors_precomp, cov3D_precomp, debug)
     finally:
         capi.set_tile_culling(True)
+        capi.set_blend_mode(0)
 
 
 def _run_ours(view, act, count, dL_dpix, colors_precomp, cov3D_precomp, debug):
