@@ -184,6 +184,14 @@ int lgr_image_l1_forward(const float* img, const float* target, int C, int H, in
 int lgr_image_loss_backward(const float* img, const float* target, const float* dmaps, int C, int H, int W, float g_l1, float g_ssim,
                             const float* grad_scale, float* d_img, void* cuda_stream);
 
+/* Push variant of lgr_backward_raw_sparse_pack for N ranks (N <= 8): every rank owns ONE exchange buffer of N slots of
+ * lgr_sparse_exchange_bytes(P) bytes each, mapped into all peers; slot_of_this_rank[r] is the address of slot `self` inside the buffer
+ * of rank r.  The packed view is written to all of them (plain stores over NVLink from inside the kernels), so after one cross-GPU
+ * barrier lgr_backward_raw_sparse_accumulate runs on the N slots of the rank's OWN buffer: no remote load is on its critical path. */
+int lgr_backward_raw_sparse_pack_push(const lgr_view* view, int P, int M, const lgr_raw_params* params, const int32_t* radii, char* geometry_blob,
+                                      void* const* slot_of_this_rank, int world, int self, void* workspace, float* dL_dmeans2D,
+                                      void* cuda_stream);
+
 /* ---- sparse view-parallel gradient exchange over peer memory ----
  * Only ~13 % of the Gaussians get a non-zero gradient from one view.  lgr_backward_raw_sparse_pack (after lgr_backward_raw_begin) runs the
  * per-Gaussian backward on those only and publishes, in `exchange_buffer` (lgr_sparse_exchange_bytes(P) bytes, 256-byte aligned, mapped into

@@ -123,6 +123,9 @@ def load():
         lib.lgr_sparse_workspace_bytes.argtypes = [i32]
         lib.lgr_backward_raw_sparse_pack.restype = i32
         lib.lgr_backward_raw_sparse_pack.argtypes = [C.POINTER(LgrView), i32, i32, C.POINTER(LgrRawParams), vp, vp, vp, vp, vp, vp]
+        lib.lgr_backward_raw_sparse_pack_push.restype = i32
+        lib.lgr_backward_raw_sparse_pack_push.argtypes = [C.POINTER(LgrView), i32, i32, C.POINTER(LgrRawParams), vp, vp, C.POINTER(C.c_void_p), i32, i32,
+                                                          vp, vp, vp]
         lib.lgr_backward_raw_sparse_accumulate.restype = i32
         lib.lgr_backward_raw_sparse_accumulate.argtypes = [i32, i32, i32, i32, C.POINTER(C.c_void_p), vp, C.POINTER(LgrRawGrads), vp]
         lib.lgr_vq_workspace_bytes.restype = C.c_size_t

@@ -315,8 +315,8 @@ __device__ __forceinline__ void back_flush(const BlendBackWarp& bw, int nbuf, in
 constexpr size_t blend_back_smem_bytes() { return sizeof(BlendRing) + 128 + 8 * sizeof(BlendBackWarp); }
 
 __global__ void __launch_bounds__(BL_THREADS)
-blend_backward_ring_kernel(const uint2* __restrict__ ranges, const float* __restrict__ rec_in, int W, int H, int tiles_x,
-                           const float* __restrict__ bg, const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib,
+blend_backward_ring_kernel(const uint2* __restrict__ ranges, const char* __restrict__ binning_blob, const int* __restrict__ listed, int W, int H,
+                           int tiles_x, const float* __restrict__ bg, const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib,
                            const float* __restrict__ dL_dpix, float* __restrict__ acc)
 {
     extern __shared__ __align__(128) unsigned char blend_dyn_smem[];
@@ -344,6 +344,9 @@ blend_backward_ring_kernel(const uint2* __restrict__ ranges, const float* __rest
     if (warp == 8) {
         // ===== producer: one thread streams the records back to front with TMA bulk loads =====
         if (lane == 0) {
+            // records = second region of the binning blob (carve_binning): right behind the 4-byte ids of the `listed` instances
+            const size_t Rn = (size_t)max(listed[0], 1);
+            const float* rec_in = reinterpret_cast<const float*>(binning_blob + (Rn * 4 + 255) / 256 * 256);
             for (uint32_t i = 0; i < nchunks; i++) {
                 const uint32_t b = nchunks - 1 - i;
                 const int s = i % BL_STAGES;

@@ -256,11 +256,23 @@ __global__ void __launch_bounds__(256) preprocess_backward_raw_kernel(RawBackArg
     const int i = first + lane;
     const size_t si = (size_t)i;
     const bool valid = lane < n;
-    const bool vis = valid && a.radii[i] > 0;
-    const bool any_vis = __any_sync(FULL, vis);
-    // the SH values are only needed for the view-direction term (degree >= 1).  A row-strided leaf (rest_stride != nrest) is
-    // not staged: the shared-memory slice holds the DENSE gradient rows, so its lanes read their coefficients from global memory
-    const bool strided = a.rest_stride != nrest;
+    // A visible Gaussian whose blend-backward accumulators are all zero (measured: 87 % of them on the bench scene -- the pixels
+    // saturate long before the deep Gaussians are reached) has exactly-zero gradients in every output: it is treated like a culled
+    // one, i.e. only its 48-byte accumulator record is read and zero rows are written.
+    bool vis = valid && a.radii[i] > 0;
+    if (vis) {
+        const float4* r4 = reinterpret_cast<const float4*>(a.acc + si * ACC_STRIDE);
+        const float4 r0 = r4[0], r1 = r4[1];
+        const float r2 = a.acc[si * ACC_STRIDE + 8];
+        vis = r0.x != 0.f || r0.y != 0.f || r0.z != 0.f || r0.w != 0.f || r1.x != 0.f || r1.y != 0.f || r1.z != 0.f || r1.w != 0.f || r2 != 0.f;
+    }
+    const unsigned live = __ballot_sync(FULL, vis);
+    const bool any_vis = live != 0;
+    // The SH values are only needed for the view-direction term (degree >= 1).  The warp's rows are staged with one TMA bulk copy
+    // only when enough of its lanes need them (>= 12 of 32: 6 KB of staging vs 192-byte rows read privately); otherwise -- and always
+    // for a row-strided leaf (rest_stride != nrest), whose staging slice holds the DENSE gradient rows -- the lanes read their own
+    // coefficients from global memory
+    const bool strided = a.rest_stride != nrest || __popc(live) < 12;
     const bool need_sh = any_vis && a.D > 0 && !strided;
     bool bulk = false;
     if (need_sh) bulk = warp_stage_sh_begin(a.rest, a.dc, nrest, first, n, s_rest, s_dc, &bars[warp], lane);

@@ -73,8 +73,27 @@ __global__ void __launch_bounds__(256) sparse_index_kernel(int P, const uint32_t
 
 // K7+K8 with the activation chain rules (the `vis` branch of preprocess_backward_raw_kernel, same arithmetic) for the t-th Gaussian of the
 // compacted list; SH coefficients come straight from global memory (the rows are scattered, there is no contiguous run to bulk-copy)
+// where a rank's packed view goes: its slot in its own exchange buffer (always) and -- push mode -- the same slot of every peer's
+// buffer, written with plain stores over NVLink while the kernel computes (posted writes: no round-trip latency on the critical path,
+// and the fast ranks' traffic overlaps the slow ranks' blend backward)
+struct SparsePush {
+    uint32_t* dst[8];  // slot base of this rank in the buffer of rank r (dst[self] = the local slot); unused entries NULL
+    int n;             // number of destinations (1 = local only)
+};
+
+// header + bitmap + prefix of the local slot -> the peers' slots (small: ~P/4 bytes per peer)
+__global__ void __launch_bounds__(256) sparse_publish_kernel(SparsePush push, int self, size_t words)
+{
+    const uint32_t* src = push.dst[self];
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < words; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t v = src[i];
+        for (int r = 0; r < push.n; r++)
+            if (r != self) push.dst[r][i] = v;
+    }
+}
+
 __global__ void __launch_bounds__(256) preprocess_backward_sparse_kernel(RawBackArgs a, const int* __restrict__ idx, const uint32_t* __restrict__ hdr,
-                                                                         float* __restrict__ rows)
+                                                                         SparsePush push, size_t rows_off)
 {
     __shared__ float s_cam[36];
     if (threadIdx.x < 16) s_cam[threadIdx.x] = a.view[threadIdx.x];
@@ -118,11 +137,14 @@ __global__ void __launch_bounds__(256) preprocess_backward_sparse_kernel(RawBack
         const float* dd = a.dc + si * 3;
         lgr::sh_backward(a.D, [&](int k) { return k < 3 ? dd[k] : rr[k - 3]; }, [](int, int, float) {}, x, y, z, cam, dRGB, dmean);
     }
-    float4* row = reinterpret_cast<float4*>(rows + (size_t)t * SPX_ROW);
-    row[0] = make_float4(dRGB[0], dRGB[1], dRGB[2], dmean[0]);
-    row[1] = make_float4(dmean[1], dmean[2], dscale[0], dscale[1]);
-    row[2] = make_float4(dscale[2], dq[0], dq[1], dq[2]);
-    row[3] = make_float4(dq[3], dop, 0.f, 0.f);
+    const float4 v0 = make_float4(dRGB[0], dRGB[1], dRGB[2], dmean[0]);
+    const float4 v1 = make_float4(dmean[1], dmean[2], dscale[0], dscale[1]);
+    const float4 v2 = make_float4(dscale[2], dq[0], dq[1], dq[2]);
+    const float4 v3 = make_float4(dq[3], dop, 0.f, 0.f);
+    for (int r = 0; r < push.n; r++) {
+        float4* row = reinterpret_cast<float4*>(reinterpret_cast<float*>(push.dst[r]) + rows_off + (size_t)t * SPX_ROW);
+        row[0] = v0; row[1] = v1; row[2] = v2; row[3] = v3;
+    }
     a.dL_dmeans2D[3 * si] = g2.dm2x; a.dL_dmeans2D[3 * si + 1] = g2.dm2y;   // dense [P,3], zero-filled by the caller; local view only
 }
 

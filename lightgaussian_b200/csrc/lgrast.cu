@@ -236,6 +236,7 @@ BinningState carve_binning(char* base, size_t R, int W, int H)
     const size_t Rn = R ? R : 1;
     Carver c(base);
     b.point_list = c.take<uint32_t>(Rn, &b.offs[0]);
+    b.records = c.take<float>(Rn * 12);   // second region: its offset, align_up(4*max(R,1), 256), is recomputed ON THE DEVICE by the backward
     b.ids_unsorted = c.take<uint32_t>(Rn);
     const size_t ksz = b.wide_keys ? 4 : 2;
     b.keys_unsorted = c.take<char>(Rn * ksz);
@@ -249,7 +250,6 @@ BinningState carve_binning(char* base, size_t R, int W, int H)
                                         (uint32_t*)nullptr, (int)Rn, 0, bits);
     b.cub_temp_bytes = bytes;
     b.cub_temp = c.take<char>(bytes);
-    b.records = c.take<float>(Rn * 12);
     b.total = align_up(c.off, 256);
     return b;
 }
@@ -1280,8 +1280,11 @@ int lgr_backward(const lgr_view* v, int P, int M, int num_rendered, const float*
         ProfScope ps(ST_BLEND_BWD, stream);
         if (g_blend_mode == 0) {
             LGR_CUDA_TRY(cudaFuncSetAttribute(blend_backward_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blend_back_smem_bytes()));
-            blend_backward_ring_kernel<<<gx * gy, BL_THREADS, blend_back_smem_bytes(), stream>>>(img.ranges, bin.records, W, H, gx, v->background, img.final_T,
-                                                                                                   img.n_contrib, dL_dout_color, geo.grad_acc);
+            // the host only knows the reference's num_rendered here; the number of LISTED instances (which fixes where the records
+            // start inside the binning blob) sits in the geometry header on the device
+            blend_backward_ring_kernel<<<gx * gy, BL_THREADS, blend_back_smem_bytes(), stream>>>(img.ranges, binning_blob, geo.num_rendered, W, H, gx,
+                                                                                                   v->background, img.final_T, img.n_contrib,
+                                                                                                   dL_dout_color, geo.grad_acc);
         } else
             blend_backward_kernel<<<gx * gy, 256, 0, stream>>>(img.ranges, bin.point_list, W, H, gx, geo.means2D, geo.conic_opacity, geo.rgb,
                                                                 v->background, img.final_T, img.n_contrib, dL_dout_color, geo.grad_acc);
@@ -1344,8 +1347,11 @@ int lgr_backward_raw_begin(const lgr_view* v, int P, int num_rendered, const int
         ProfScope ps(ST_BLEND_BWD, stream);
         if (g_blend_mode == 0) {
             LGR_CUDA_TRY(cudaFuncSetAttribute(blend_backward_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blend_back_smem_bytes()));
-            blend_backward_ring_kernel<<<gx * gy, BL_THREADS, blend_back_smem_bytes(), stream>>>(img.ranges, bin.records, W, H, gx, v->background, img.final_T,
-                                                                                                   img.n_contrib, dL_dout_color, geo.grad_acc);
+            // the host only knows the reference's num_rendered here; the number of LISTED instances (which fixes where the records
+            // start inside the binning blob) sits in the geometry header on the device
+            blend_backward_ring_kernel<<<gx * gy, BL_THREADS, blend_back_smem_bytes(), stream>>>(img.ranges, binning_blob, geo.num_rendered, W, H, gx,
+                                                                                                   v->background, img.final_T, img.n_contrib,
+                                                                                                   dL_dout_color, geo.grad_acc);
         } else
             blend_backward_kernel<<<gx * gy, 256, 0, stream>>>(img.ranges, bin.point_list, W, H, gx, geo.means2D, geo.conic_opacity, geo.rgb,
                                                                 v->background, img.final_T, img.n_contrib, dL_dout_color, geo.grad_acc);
@@ -1448,18 +1454,38 @@ size_t lgr_sparse_workspace_bytes(int P)
 int lgr_backward_raw_sparse_pack(const lgr_view* v, int P, int M, const lgr_raw_params* params, const int32_t* radii, char* geometry_blob,
                                  void* exchange_buffer, void* workspace, float* dL_dmeans2D, void* cuda_stream)
 {
+    void* only[1] = {exchange_buffer};
+    return lgr_backward_raw_sparse_pack_push(v, P, M, params, radii, geometry_blob, only, 1, 0, workspace, dL_dmeans2D, cuda_stream);
+}
+
+// push mode: slot_of_this_rank[r] = this rank's slot inside the exchange buffer of rank r (peer-mapped for r != self); the packed view
+// (header, bitmap, prefix, rows) lands in all of them, so that after ONE cross-GPU barrier every rank accumulates from LOCAL memory.
+int lgr_backward_raw_sparse_pack_push(const lgr_view* v, int P, int M, const lgr_raw_params* params, const int32_t* radii, char* geometry_blob,
+                                      void* const* slot_of_this_rank, int world, int self, void* workspace, float* dL_dmeans2D,
+                                      void* cuda_stream)
+{
     cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
     if (P == 0) return LGR_OK;
-    if (!v || P < 0 || M < 1 || !params || !radii || !geometry_blob || !exchange_buffer || !workspace || !dL_dmeans2D ||
-        ((uintptr_t)exchange_buffer & 255) || ((uintptr_t)workspace & 255) || ((uintptr_t)params->rotation & 15)) {
-        g_last_error = "lgr_backward_raw_sparse_pack: missing argument or misaligned buffer (exchange buffer and workspace: 256 bytes)";
+    if (!v || P < 0 || M < 1 || !params || !radii || !geometry_blob || !slot_of_this_rank || world < 1 || world > 8 || self < 0 || self >= world ||
+        !workspace || !dL_dmeans2D || ((uintptr_t)workspace & 255) || ((uintptr_t)params->rotation & 15)) {
+        g_last_error = "lgr_backward_raw_sparse_pack: missing argument, more than 8 ranks, or misaligned buffer (exchange buffers and workspace: 256 bytes)";
         return LGR_ERR_INVALID_ARG;
+    }
+    SparsePush push;
+    memset(&push, 0, sizeof(push));
+    push.n = world;
+    for (int r = 0; r < world; r++) {
+        if (!slot_of_this_rank[r] || ((uintptr_t)slot_of_this_rank[r] & 255)) {
+            g_last_error = "lgr_backward_raw_sparse_pack: exchange slot missing or not 256-byte aligned";
+            return LGR_ERR_INVALID_ARG;
+        }
+        push.dst[r] = static_cast<uint32_t*>(slot_of_this_rank[r]);
     }
     const bool debug = v->debug != 0;
     const int W = v->image_width, H = v->image_height;
     GeometryState geo = carve_geometry(geometry_blob, (size_t)P);
     const SparseLayout L = sparse_layout(P);
-    uint32_t* xb = static_cast<uint32_t*>(exchange_buffer);
+    uint32_t* xb = push.dst[self];
     const int w32 = (P + 31) / 32;
     char* ws = static_cast<char*>(workspace);
     uint32_t* popc = reinterpret_cast<uint32_t*>(ws);
@@ -1488,7 +1514,8 @@ int lgr_backward_raw_sparse_pack(const lgr_view* v, int P, int M, const lgr_raw_
         sparse_flag_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, radii, geo.grad_acc, xb + L.bitmap, popc);
         LGR_CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, popc, xb + L.prefix, w32, stream));
         sparse_index_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, xb + L.bitmap, xb + L.prefix, idx, xb + L.hdr, v->campos);
-        preprocess_backward_sparse_kernel<<<(P + 255) / 256, 256, 0, stream>>>(a, idx, xb + L.hdr, reinterpret_cast<float*>(xb + L.rows));
+        if (world > 1) sparse_publish_kernel<<<148, 256, 0, stream>>>(push, self, L.rows);
+        preprocess_backward_sparse_kernel<<<(P + 255) / 256, 256, 0, stream>>>(a, idx, xb + L.hdr, push, L.rows);
     }
     LGR_LAUNCH_CHECK("preprocess_backward_sparse_kernel", debug, stream);
     return LGR_OK;

@@ -510,17 +510,24 @@ def _symm_exchange(device, P, world, group):
 
 class _SparseExchange:
     """Two alternating exchange buffers per rank in NVLink symmetric memory (torch.distributed._symmetric_memory), each mapped into every
-    peer, for the sparse gradient exchange (csrc/lgr_sparse.cuh).  Buffer k of step s is rewritten at step s+2; every rank passes the
-    barrier of step s+1 only after its accumulate kernel of step s has finished, so one cross-GPU barrier per step is enough.
-    world == 1 (tests): plain device tensors, no barrier."""
+    peer, for the sparse gradient exchange (csrc/lgr_sparse.cuh).  A buffer holds `world` slots; slot v carries view v's packed gradient
+    (header | bitmap | prefix | 64-byte rows).
+      push (default): rank r WRITES its packed view into slot r of every rank's buffer from inside the pack kernels (posted stores over
+                      NVLink, overlapping the slower ranks' blend backward); after one barrier every rank accumulates from LOCAL memory.
+      pull (LGR_EXCHANGE_PUSH=0, the round-1 scheme): rank r writes slot r of its OWN buffer only; after the barrier the accumulate
+                      kernel loads every peer's slot over NVLink.
+    Buffer k of step s is rewritten at step s+2; every rank passes the barrier of step s+1 only after its accumulate kernel of step s
+    has finished, so one cross-GPU barrier per step is enough.  world == 1 (tests): plain device tensors, no barrier."""
 
     def __init__(self, device, P, world, group):
         lib = capi.load()
         if world > 8:
             raise RuntimeError("the sparse peer-memory exchange supports at most 8 ranks (one NVSwitch domain)")
         self.world = world
-        self.capacity = P          # the layout inside the buffers is computed from each call's P <= capacity
-        n = (int(lib.lgr_sparse_exchange_bytes(P)) + 3) // 4
+        self.capacity = P          # the layout inside a slot is computed from each call's P <= capacity
+        self.push = world > 1 and _os.environ.get("LGR_EXCHANGE_PUSH", "1") != "0"
+        slot = (int(lib.lgr_sparse_exchange_bytes(P)) + 255) // 256 * 256
+        n = world * slot // 4
         self.ws = torch.empty(int(lib.lgr_sparse_workspace_bytes(P)), dtype=torch.uint8, device=device)
         if world > 1:
             import torch.distributed as dist
@@ -529,21 +536,37 @@ class _SparseExchange:
             self.bufs = [symm_mem.empty(n, dtype=torch.float32, device=device) for _ in range(2)]
             self.hdls = [symm_mem.rendezvous(b, grp.group_name) for b in self.bufs]
             assert int(self.hdls[0].world_size) == world
-            tables = [[int(p) for p in h.buffer_ptrs] for h in self.hdls]
+            self.rank = int(self.hdls[0].rank)
+            bases = [[int(p) for p in h.buffer_ptrs] for h in self.hdls]
         else:
             self.bufs = [torch.empty(n, dtype=torch.float32, device=device) for _ in range(2)]
             self.hdls = [None, None]
-            tables = [[b.data_ptr()] for b in self.bufs]
+            self.rank = 0
+            bases = [[b.data_ptr()] for b in self.bufs]
         for b in self.bufs:
             b.zero_()
-        for t in tables:
+        for t in bases:
             assert len(t) == world and all(t) and all(p % 256 == 0 for p in t)
-        self.ptr_tables = [(C.c_void_p * world)(*t) for t in tables]
+        r = self.rank
+        # pack: where this rank's view goes.  accumulate: where view v is read from.
+        if self.push:
+            self.pack_tables = [(C.c_void_p * world)(*[t[q] + r * slot for q in range(world)]) for t in bases]
+            self.ptr_tables = [(C.c_void_p * world)(*[t[r] + v * slot for v in range(world)]) for t in bases]
+        else:
+            self.pack_tables = [(C.c_void_p * 1)(t[r] + r * slot) for t in bases]
+            self.ptr_tables = [(C.c_void_p * world)(*[t[v] + v * slot for v in range(world)]) for t in bases]
+        self.slot_bytes = slot
         self.turn = 0
 
     def next(self):
         self.turn ^= 1
         return self.turn
+
+    def rows_published(self) -> int:
+        """rows this rank packed in its last backward (diagnostics)"""
+        k, r = self.turn, self.rank
+        off = r * self.slot_bytes // 4
+        return int(self.bufs[k][off + 3:off + 4].view(torch.int32).item())
 
 
 _sparse_cache = {}
@@ -586,8 +609,7 @@ def exchange_info(world):
         return "none", None
     for (dev, w), xs in _sparse_cache.items():
         if w == world and xs is not None:
-            rows = int(xs.bufs[xs.turn][3:4].view(torch.int32).item())
-            return "sparse-p2p", rows
+            return ("sparse-p2p-push" if xs.push else "sparse-p2p"), xs.rows_published()
     return "dense-nccl", None
 
 
@@ -611,9 +633,10 @@ def _backward_raw_sparse(xs, rs, num_rendered, grad_out_color, xyz, dc, rest, sc
                                         img.data_ptr(), dpix.data_ptr(), None, main.cuda_stream)
         capi.check(st, "lgr_backward_raw_begin")
         params = _raw_struct(xyz, dc, rest, scaling, rotation, opacity)
-        st = lib.lgr_backward_raw_sparse_pack(C.byref(view), P, M, C.byref(params), radii.data_ptr(), geom.data_ptr(), xs.bufs[k].data_ptr(),
-                                              xs.ws.data_ptr(), g2d.data_ptr(), main.cuda_stream)
-        capi.check(st, "lgr_backward_raw_sparse_pack")
+        st = lib.lgr_backward_raw_sparse_pack_push(C.byref(view), P, M, C.byref(params), radii.data_ptr(), geom.data_ptr(), xs.pack_tables[k],
+                                                   len(xs.pack_tables[k]), xs.rank if xs.push else 0, xs.ws.data_ptr(), g2d.data_ptr(),
+                                                   main.cuda_stream)
+        capi.check(st, "lgr_backward_raw_sparse_pack_push")
         if world > 1:
             xs.hdls[k].barrier(channel=0)          # every rank's rows of this step are published
         grads = _raw_grads_struct(*g)
