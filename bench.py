@@ -49,6 +49,8 @@ def parse_args():
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--cams", type=int, default=16, help="distinct synthetic cameras cycled through")
     ap.add_argument("--blend-mode", type=int, default=0, help="DIAGNOSTIC: 0 = ring blend kernels (default), 1 = the round-1 blend kernels")
+    ap.add_argument("--bin-mode", type=int, default=0, help="DIAGNOSTIC: 0 = hand-written binning, estimated blob size (default), 1 = exact blob "
+                    "size (one stream sync), 2 = the round-1 library sorts")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -396,6 +398,7 @@ def main():
         from lightgaussian_b200.renderer import render as render_fn
         capi.load()
         capi.set_blend_mode(args.blend_mode)
+        capi.set_binning_mode(args.bin_mode)
         kind = None
     elif stock is not None:
         render_fn, kind = stock[0], "reference"
@@ -612,6 +615,10 @@ def main():
             "preprocess_kernel": 12 * P + Pv * (32 + 12 * M) + 4 * P + 40 * Pv,
             "depth_sort(cub)": 16 * P, "scan(cub)": 8 * P, "emit_kernel": 12 * Pv + 6 * R, "tile_sort(cub)": 12 * R,
             "ranges_kernel": 2 * R,
+            # hand-written binning (csrc/lgr_bin.cuh): keys+ids read and written once; 16-byte bin record + id per Gaussian read by the
+            # count and by the scatter, 4 bytes per listed instance written (R here = the reference's num_rendered >= instances listed)
+            "depth_sort(dsort_count+bin_scan+dsort_scatter x3)": 16 * P, "tile_count_kernel+bin_scan_kernel": 20 * P,
+            "tile_scatter_kernel": 20 * P + 4 * R,
             "blend_forward_kernel": 40 * R + 20 * N,
             "blend_backward_kernel": 20 * N + 40 * R + 44 * Pv,
             "preprocess_backward_kernel": 44 * Pv + 12 * P + Pv * (32 + 12 * M) + P * (56 + 12 * M),
@@ -816,6 +823,9 @@ def main():
                              "reference-compatible API path" if args.impl == "ours" else kind)},
             "clocks": clocks, "gpu_launches": launches,
         }
+        if args.impl == "ours":
+            line["run"]["binning"] = {"mode": args.bin_mode, "repeats_for_capacity": capi.binning_overflows(),
+                                      "what": "views whose binning blob estimate was too small (scatter + blend repeated), whole run"}
         if args.impl != "ours":
             line["impl"] = args.impl
             line["e2e"] = {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}

@@ -285,10 +285,27 @@ uint64_t lgr_launch_count(void);
  * backward must run in the mode its forward ran in (the ring backward streams the records the ring forward stored). */
 int lgr_set_blend_mode(int mode);
 
+/* Binning (per-tile depth-ordered instance lists; replaces the scan + 64-bit radix sort of RAST/cuda_rasterizer/rasterizer_impl.cu:278-319
+ * and its blocking device-to-host copy of num_rendered at :282).  0 (default) = hand-written kernels (csrc/lgr_bin.cuh): the binning
+ * allocator is called BEFORE the instance count is known, with a size from a running estimate; the kernels bound their stores by that
+ * capacity, the host reads the count while the blend kernel is already running and repeats scatter + blend with an exactly sized blob
+ * (a second binning_alloc call) when the estimate was too small.  1 = the same kernels, blob sized exactly after a stream
+ * synchronisation (one binning_alloc call, the reference's behaviour).  2 = the round-1 path (library radix sorts + scan, host
+ * synchronisation); also used automatically above 49 152 tiles.  Process-wide.  lgr_binning_overflows() = views that took the repeat. */
+int lgr_set_binning_mode(int mode);
+uint64_t lgr_binning_overflows(void);
+void lgr_set_binning_estimate(uint64_t instances);   /* overwrite the running estimate of mode 0 (tests; 0 = forget) */
+
+/* Diagnostics / A-B: the fused K7+K8 of lgr_backward_raw for a whole view with dense outputs.  0 (default) = one pass zero-fills all
+ * output rows (TMA bulk stores) and lists the Gaussians whose accumulators are non-zero, a second kernel runs K7+K8 on that list;
+ * 1 = the dense one-warp-per-32-Gaussians kernel. */
+int lgr_set_kback_mode(int mode);
+
 /* Exact tile-level culling at binning time (default on): (tile, Gaussian) instances in which no pixel can reach
  * alpha >= 1/255 are not listed.  Images, gradients and significance are unchanged; only the internal lists shrink.
  * Turn it off to obtain per-tile lists identical to the reference's (tests).  num_rendered always reports the
- * reference's value.  The geometry blob starts with two int32: [0] instances listed, [1] the reference's num_rendered. */
+ * reference's value.  The geometry blob starts with int32 words: [0] instances listed, [1] the reference's num_rendered,
+ * [2] instances the binning blob was sized for, [3] capacity overflow flag (0 once a forward call has returned). */
 int lgr_set_tile_culling(int on);
 
 /* Optional per-stage device timing: when enabled every launch is bracketed by CUDA events on its stream.

@@ -11,7 +11,7 @@ CSRC = os.path.join(_HERE, "csrc")
 LIB_DIR = os.path.join(_HERE, "_lib")
 LIB_PATH = os.path.join(LIB_DIR, "liblgrast.so")
 SOURCES = ["lgrast.cu"]
-HEADERS = ["lgr_math.cuh", "lgr_raw.cuh", "lgr_sparse.cuh", "lgr_loss.cuh", "lgr_optim.cuh", "lgr_vq.cuh", os.path.join("..", "..", "include", "lgrast.h")]
+HEADERS = ["lgr_math.cuh", "lgr_blend.cuh", "lgr_raw.cuh", "lgr_sparse.cuh", "lgr_loss.cuh", "lgr_optim.cuh", "lgr_vq.cuh", os.path.join("..", "..", "include", "lgrast.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

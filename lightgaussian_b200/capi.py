@@ -148,6 +148,9 @@ def load():
         lib.lgr_mark_visible.argtypes = [i32, vp, vp, vp, vp, vp]
         lib.lgr_last_error.restype = C.c_char_p
         lib.lgr_launch_count.restype = C.c_uint64
+        lib.lgr_binning_overflows.restype = C.c_uint64
+        lib.lgr_set_binning_estimate.restype = None
+        lib.lgr_set_binning_estimate.argtypes = [C.c_uint64]
         for name in ("lgr_geometry_layout", "lgr_image_layout", "lgr_binning_layout"):
             getattr(lib, name).restype = C.c_size_t
         lib.lgr_geometry_layout.argtypes = [i32, C.POINTER(C.c_size_t), i32]
@@ -244,6 +247,27 @@ def binning_layout(R: int, W: int, H: int):
 def set_blend_mode(mode: int) -> None:
     """0 = ring kernels (default), 1 = round-1 kernels (A/B measurements)"""
     check(load().lgr_set_blend_mode(int(mode)), "lgr_set_blend_mode")
+
+
+def set_binning_mode(mode: int) -> None:
+    """0 = hand-written binning kernels with an estimated blob size (default), 1 = the same with an exact size (one stream sync),
+    2 = the round-1 library sorts"""
+    check(load().lgr_set_binning_mode(int(mode)), "lgr_set_binning_mode")
+
+
+def binning_overflows() -> int:
+    """views whose binning blob estimate was too small (scatter + blend repeated) since load"""
+    return int(load().lgr_binning_overflows())
+
+
+def set_kback_mode(mode: int) -> None:
+    """fused K7+K8 of the raw backward: 0 = zero-fill + compacted list (default), 1 = dense kernel (A/B measurements)"""
+    check(load().lgr_set_kback_mode(int(mode)), "lgr_set_kback_mode")
+
+
+def set_binning_estimate(instances: int) -> None:
+    """overwrite the running instance estimate of binning mode 0 (tests; 0 = forget it)"""
+    load().lgr_set_binning_estimate(C.c_uint64(int(instances)))
 
 
 def set_tile_culling(on: bool):

@@ -1,0 +1,360 @@
+// lgr_bin.cuh -- hand-written binning (round 2): the per-tile, depth-ordered instance lists without any library sort / scan,
+// without the unsorted key / id arrays and without a host synchronisation in the middle.
+//
+// What must come out (RAST/cuda_rasterizer/rasterizer_impl.cu:70-138, 278-319): for every 16x16 tile the Gaussians that overlap
+// it, ordered by (depth bits, Gaussian id) -- the order of the reference's stable 64-bit sort on (tile << 32 | depth).
+//
+//   1. depth order of the P Gaussians: LSD radix sort of the 32-bit depth keys in THREE passes of 11 / 11 / 10 bits (the library
+//      sort took four 8-bit passes), ids implicit in the first pass, keys dropped in the last.
+//   2. tile bucketing: ONE stable counting-sort pass over the (up to 50 000) tile indices.  Instances are never materialised
+//      unsorted: a count kernel and a scatter kernel both regenerate them from the 16-byte per-Gaussian bin record
+//      (tile rectangle + exact 64-bit keep mask, written by the preprocess kernel) walking the Gaussians in depth order.
+//
+// Every pass is the same three-kernel pattern on a count matrix M[BIN_V blocks][bins]:
+//      count    block b histograms ITS contiguous chunk of the input in shared memory -> row b of M
+//      scan     M[b][bin] <- sum over b' < b (exclusive, per bin); the last block to finish turns the bin totals into bin bases
+//               (and, for the tile pass, writes the per-tile ranges, the instance total and the capacity-overflow flag)
+//      scatter  block b re-reads its chunk IN ORDER; destination = base[bin] + M[b][bin] + (rank among the block's earlier items
+//               of that bin).  The rank comes from a shared-memory cursor per bin that the block's warps update in their input
+//               order: warps take turns (a shared ticket), inside a turn one __match_any_sync groups the 32 items of a step,
+//               the lowest lane of each group bumps the cursor and the others add their position in the group.  Loads, the
+//               instance generation and the global stores of different warps overlap; only the cursor update is serial.
+//
+// The instance count R is needed on the host only to size the binning blob.  The blob is sized from a running estimate BEFORE the
+// count is known; the kernels bound every store by that capacity and raise a flag when it is too small, the host looks at the
+// count (a 16-byte copy that arrives while the blend kernel is already running) and repeats the scatter and the blend in the
+// rare case of an overflow.  The GPU never idles on the host.
+#pragma once
+
+namespace {
+
+constexpr int BIN_V = 592;            // blocks of every count / scatter kernel = rows of the count matrix (148 SMs x 4)
+constexpr int DS_BITS = 11;
+constexpr int DS_BINS = 1 << DS_BITS;
+constexpr uint32_t BIN_NONE = 0xffffffffu;
+constexpr int TB_THREADS = 128;       // tile count / scatter block: 4 warps
+constexpr int BIN_MAX_TILES = 49152;  // shared-memory cursor per tile (4 B): above this the library path is used
+
+__host__ __device__ inline int bin_pad(int bins) { return (bins + 255) / 256 * 256; }
+inline int bin_per_block(int P) { return ((P + BIN_V - 1) / BIN_V + 127) / 128 * 128; }
+
+// header words at the start of the geometry blob
+enum { HDR_LISTED = 0, HDR_RENDERED = 1, HDR_CAPACITY = 2, HDR_OVERFLOW = 3, HDR_DONE = 8, HDR_LIVE = 9 };
+
+// ------------------------------------------------------------------------------------------------
+// depth sort: one LSD pass = count -> scan -> scatter
+// ------------------------------------------------------------------------------------------------
+template <int SHIFT, bool FIRST>
+__global__ void __launch_bounds__(256) dsort_count_kernel(const uint32_t* __restrict__ keys, int P, int per_block, uint32_t* __restrict__ M,
+                                                          int* __restrict__ header)
+{
+    __shared__ uint32_t hist[DS_BINS];
+    for (int i = threadIdx.x; i < DS_BINS; i += 256) hist[i] = 0;
+    if (FIRST && blockIdx.x == 0 && threadIdx.x < 16) header[threadIdx.x] = 0;
+    __syncthreads();
+    const int lo = blockIdx.x * per_block, hi = min(P, lo + per_block);
+    const int lane = threadIdx.x & 31;
+    for (int k0 = lo + (threadIdx.x & ~31); k0 < hi; k0 += 256) {
+        const int k = k0 + lane;
+        const uint32_t d = k < hi ? ((keys[k] >> SHIFT) & (DS_BINS - 1)) : BIN_NONE;
+        const unsigned m = __match_any_sync(FULL, d);   // the top pass has a handful of distinct digits: aggregate per warp
+        if (d != BIN_NONE && lane == __ffs(m) - 1) atomicAdd(&hist[d], (uint32_t)__popc(m));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < DS_BINS; i += 256) M[(size_t)blockIdx.x * DS_BINS + i] = hist[i];
+}
+
+struct BinScanArgs {
+    uint32_t* M;          // [V][bins_pad] counts in, exclusive prefixes over the blocks out
+    int V, bins, bins_pad;
+    uint32_t* bin_total;  // [bins_pad] scratch
+    uint32_t* bin_base;   // [bins_pad] out: exclusive scan of the bin totals
+    int* header;          // geometry header (done counter; tile pass: totals and flags)
+    uint2* ranges;        // tile pass: [bins] per-tile [start, end)
+    uint32_t capacity;    // tile pass: instances the binning blob can hold
+};
+
+template <bool TILES>
+__global__ void __launch_bounds__(256) bin_scan_kernel(BinScanArgs a)
+{
+    __shared__ uint32_t part[8][32];
+    __shared__ uint32_t wsum[8];
+    __shared__ bool last;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int bin = blockIdx.x * 32 + lane;   // gridDim.x = bins_pad / 32
+    const int rows_per = (a.V + 7) / 8;
+    const int r0 = warp * rows_per, r1 = min(a.V, r0 + rows_per);
+    uint32_t* col = a.M + bin;
+    const size_t stride = (size_t)a.bins_pad;
+    uint32_t s = 0;
+    {
+        int r = r0;
+        for (; r + 8 <= r1; r += 8) {
+            uint32_t v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) v[u] = col[(size_t)(r + u) * stride];
+#pragma unroll
+            for (int u = 0; u < 8; u++) s += v[u];
+        }
+        for (; r < r1; r++) s += col[(size_t)r * stride];
+    }
+    part[warp][lane] = s;
+    __syncthreads();
+    uint32_t run = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) {
+        const uint32_t v = part[w][lane];
+        if (w < warp) run += v;
+        total += v;
+    }
+    {
+        int r = r0;
+        for (; r + 8 <= r1; r += 8) {
+            uint32_t v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) v[u] = col[(size_t)(r + u) * stride];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                col[(size_t)(r + u) * stride] = run;
+                run += v[u];
+            }
+        }
+        for (; r < r1; r++) {
+            const uint32_t v = col[(size_t)r * stride];
+            col[(size_t)r * stride] = run;
+            run += v;
+        }
+    }
+    if (warp == 0) a.bin_total[bin] = total;
+
+    // the last block to arrive scans the bin totals
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(reinterpret_cast<unsigned*>(a.header + HDR_DONE), 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    const int chunk = a.bins_pad / 256;   // consecutive bins per thread
+    const int c0 = threadIdx.x * chunk;
+    uint32_t mine = 0;
+    for (int i = 0; i < chunk; i++) mine += __ldcg(a.bin_total + c0 + i);
+    uint32_t incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(FULL, incl, d);
+        if (lane >= d) incl += t;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    uint32_t base = incl - mine;
+    for (int w = 0; w < warp; w++) base += wsum[w];
+    for (int i = 0; i < chunk; i++) {
+        const uint32_t c = __ldcg(a.bin_total + c0 + i);
+        a.bin_base[c0 + i] = base;
+        if (TILES && c0 + i < a.bins) a.ranges[c0 + i] = c ? make_uint2(base, base + c) : make_uint2(0u, 0u);   // empty tiles: (0,0), the reference's memset
+        base += c;
+    }
+    if (threadIdx.x == 255) {
+        if (TILES) {
+            a.header[HDR_LISTED] = (int)base;
+            a.header[HDR_CAPACITY] = (int)a.capacity;
+            a.header[HDR_OVERFLOW] = base > a.capacity ? 1 : 0;
+        }
+        a.header[HDR_DONE] = 0;   // ready for the next pass
+    }
+}
+
+constexpr int DS_ITEMS = 4;   // keys per lane and turn: a warp ranks 128 consecutive keys per turn
+
+template <int SHIFT, bool FIRST, bool LAST>
+__global__ void __launch_bounds__(256) dsort_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ ids_in,
+                                                            uint32_t* __restrict__ keys_out, uint32_t* __restrict__ ids_out,
+                                                            const uint32_t* __restrict__ E, const uint32_t* __restrict__ bin_base, int P, int per_block)
+{
+    __shared__ uint32_t cursor[DS_BINS];
+    __shared__ int turn;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < DS_BINS; i += 256) cursor[i] = bin_base[i] + E[(size_t)blockIdx.x * DS_BINS + i];
+    if (threadIdx.x == 0) turn = 0;
+    __syncthreads();
+    const int lo = blockIdx.x * per_block, hi = min(P, lo + per_block);
+    const int nturns = (hi - lo + 32 * DS_ITEMS - 1) / (32 * DS_ITEMS);
+    const unsigned lt = (1u << lane) - 1u;
+    for (int t = warp; t < nturns; t += 8) {
+        const int base = lo + t * 32 * DS_ITEMS;
+        uint32_t key[DS_ITEMS], id[DS_ITEMS], d[DS_ITEMS];
+        unsigned m[DS_ITEMS];
+#pragma unroll
+        for (int j = 0; j < DS_ITEMS; j++) {
+            const int k = base + j * 32 + lane;
+            const bool valid = k < hi;
+            key[j] = valid ? keys_in[k] : 0u;
+            id[j] = FIRST ? (uint32_t)k : (valid ? ids_in[k] : 0u);
+            d[j] = valid ? ((key[j] >> SHIFT) & (DS_BINS - 1)) : BIN_NONE;
+            m[j] = __match_any_sync(FULL, d[j]);
+        }
+        if (lane == 0)
+            while (*reinterpret_cast<volatile int*>(&turn) != t) {}
+        __syncwarp();
+        uint32_t pos[DS_ITEMS];
+#pragma unroll
+        for (int j = 0; j < DS_ITEMS; j++) {
+            const int leader = __ffs(m[j]) - 1;
+            uint32_t old = 0;
+            if (lane == leader && d[j] != BIN_NONE) {
+                old = cursor[d[j]];
+                cursor[d[j]] = old + (uint32_t)__popc(m[j]);
+            }
+            __syncwarp();
+            pos[j] = __shfl_sync(FULL, old, leader) + (uint32_t)__popc(m[j] & lt);
+        }
+        __threadfence_block();
+        __syncwarp();
+        if (lane == 0) *reinterpret_cast<volatile int*>(&turn) = t + 1;
+#pragma unroll
+        for (int j = 0; j < DS_ITEMS; j++)
+            if (d[j] != BIN_NONE) {
+                if (!LAST) keys_out[pos[j]] = key[j];
+                ids_out[pos[j]] = id[j];
+            }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// tile bucketing
+// ------------------------------------------------------------------------------------------------
+// bin record of a Gaussian (written by the preprocess kernels):  x = x0 | y0 << 16   y = w | h << 16   (z, w) = 64-bit keep mask.
+// Tile b (row-major inside the w x h rectangle) is listed iff bit b is set; rectangles above 64 tiles are listed whole (mask all ones).
+// Culled Gaussians have w = h = 0.
+__device__ __forceinline__ uint4 make_bin_rec(int x0, int y0, int w, int h, unsigned long long mask)
+{
+    return make_uint4((uint32_t)x0 | ((uint32_t)y0 << 16), (uint32_t)w | ((uint32_t)h << 16), (uint32_t)mask, (uint32_t)(mask >> 32));
+}
+
+struct BinRow {   // one lane's Gaussian of a 32-Gaussian row
+    uint32_t id, cnt, off, total, area;
+    int x0, y0, w;
+    unsigned long long mask;
+};
+
+__device__ __forceinline__ void bin_row_load(const uint32_t* __restrict__ sorted_ids, const uint4* __restrict__ bin_rec, int k, int kend, int lane, BinRow& r)
+{
+    r.id = 0; r.cnt = 0; r.area = 0; r.x0 = 0; r.y0 = 0; r.w = 1; r.mask = ~0ull;
+    if (k < kend) {
+        r.id = sorted_ids[k];
+        const uint4 q = __ldg(bin_rec + r.id);
+        const int w = (int)(q.y & 0xffffu), h = (int)(q.y >> 16);
+        r.area = (uint32_t)(w * h);
+        if (r.area) {
+            r.x0 = (int)(q.x & 0xffffu); r.y0 = (int)(q.x >> 16); r.w = w;
+            r.mask = (unsigned long long)q.z | ((unsigned long long)q.w << 32);
+            r.cnt = r.area > 64u ? r.area : (uint32_t)__popcll(r.mask);
+        }
+    }
+    uint32_t incl = r.cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(FULL, incl, d);
+        if (lane >= d) incl += t;
+    }
+    r.off = incl - r.cnt;
+    r.total = __shfl_sync(FULL, incl, 31);
+}
+
+// instance j (row-local, j < r.total for valid lanes) -> tile index and owner id; BIN_NONE for lanes past the end
+__device__ __forceinline__ uint32_t bin_row_instance(const BinRow& r, uint32_t j, int gx, uint32_t& owner_id)
+{
+    int lo = 0, hi = 31;   // largest lane m with off[m] <= j
+#pragma unroll
+    for (int it = 0; it < 5; it++) {
+        const int mid = (lo + hi + 1) >> 1;
+        const uint32_t v = __shfl_sync(FULL, r.off, mid);
+        if (v <= j) lo = mid;
+        else hi = mid - 1;
+    }
+    const uint32_t o_off = __shfl_sync(FULL, r.off, lo);
+    owner_id = __shfl_sync(FULL, r.id, lo);
+    const int o_x0 = __shfl_sync(FULL, r.x0, lo), o_y0 = __shfl_sync(FULL, r.y0, lo), o_w = __shfl_sync(FULL, r.w, lo);
+    const unsigned long long o_mask = __shfl_sync(FULL, r.mask, lo);
+    if (j >= r.total) return BIN_NONE;
+    int local = (int)(j - o_off);
+    if (o_mask != ~0ull) {   // local-th kept tile of the rectangle
+        const uint32_t mlo = (uint32_t)o_mask;
+        const int clo = __popc(mlo);
+        local = local < clo ? (int)__fns(mlo, 0, local + 1) : 32 + (int)__fns((uint32_t)(o_mask >> 32), 0, local - clo + 1);
+    }
+    const int ry = (int)__fdividef((float)local + 0.5f, (float)o_w);   // exact: |error| << 0.5 / w for rectangles of a few thousand tiles
+    const int rx = local - ry * o_w;
+    return (uint32_t)((o_y0 + ry) * gx + (o_x0 + rx));
+}
+
+__global__ void __launch_bounds__(TB_THREADS) tile_count_kernel(const uint32_t* __restrict__ sorted_ids, const uint4* __restrict__ bin_rec, int P,
+                                                                int per_block, int gx, int tiles_pad, uint32_t* __restrict__ M, int* __restrict__ header)
+{
+    extern __shared__ uint32_t tb_smem[];
+    uint32_t* hist = tb_smem;
+    for (int i = threadIdx.x; i < tiles_pad; i += TB_THREADS) hist[i] = 0;
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int lo = blockIdx.x * per_block, hi = min(P, lo + per_block);
+    uint32_t area = 0;
+    for (int row = lo + warp * 32; row < hi; row += (TB_THREADS / 32) * 32) {
+        BinRow r;
+        bin_row_load(sorted_ids, bin_rec, row + lane, hi, lane, r);
+        area += r.area;
+        for (uint32_t base = 0; base < r.total; base += 32) {
+            uint32_t owner;
+            const uint32_t tile = bin_row_instance(r, base + lane, gx, owner);
+            if (tile != BIN_NONE) atomicAdd(&hist[tile], 1u);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < tiles_pad; i += TB_THREADS) M[(size_t)blockIdx.x * tiles_pad + i] = hist[i];
+    // the reference's num_rendered = sum of the rectangle areas (rasterizer_impl.cu:278-283)
+    area = __reduce_add_sync(FULL, area);
+    if (lane == 0 && area) atomicAdd(reinterpret_cast<unsigned*>(header + HDR_RENDERED), area);
+}
+
+__global__ void __launch_bounds__(TB_THREADS) tile_scatter_kernel(const uint32_t* __restrict__ sorted_ids, const uint4* __restrict__ bin_rec, int P,
+                                                                  int per_block, int gx, int tiles_pad, const uint32_t* __restrict__ E,
+                                                                  const uint32_t* __restrict__ bin_base, const int* __restrict__ header,
+                                                                  uint32_t* __restrict__ point_list)
+{
+    extern __shared__ uint32_t tb_smem[];
+    uint32_t* cursor = tb_smem;
+    __shared__ int turn;
+    for (int i = threadIdx.x; i < tiles_pad; i += TB_THREADS) cursor[i] = bin_base[i] + E[(size_t)blockIdx.x * tiles_pad + i];
+    if (threadIdx.x == 0) turn = 0;
+    __syncthreads();
+    const uint32_t capacity = (uint32_t)header[HDR_CAPACITY];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int lo = blockIdx.x * per_block, hi = min(P, lo + per_block);
+    const int nrows = (hi - lo + 31) / 32;
+    const unsigned lt = (1u << lane) - 1u;
+    for (int t = warp; t < nrows; t += TB_THREADS / 32) {
+        BinRow r;
+        bin_row_load(sorted_ids, bin_rec, lo + t * 32 + lane, hi, lane, r);
+        if (lane == 0)
+            while (*reinterpret_cast<volatile int*>(&turn) != t) {}
+        __syncwarp();
+        for (uint32_t base = 0; base < r.total; base += 32) {
+            uint32_t owner;
+            const uint32_t tile = bin_row_instance(r, base + lane, gx, owner);
+            const unsigned m = __match_any_sync(FULL, tile);
+            const int leader = __ffs(m) - 1;
+            uint32_t old = 0;
+            if (lane == leader && tile != BIN_NONE) {
+                old = cursor[tile];
+                cursor[tile] = old + (uint32_t)__popc(m);
+            }
+            __syncwarp();
+            const uint32_t pos = __shfl_sync(FULL, old, leader) + (uint32_t)__popc(m & lt);
+            if (tile != BIN_NONE && pos < capacity) point_list[pos] = owner;
+        }
+        __threadfence_block();
+        __syncwarp();
+        if (lane == 0) *reinterpret_cast<volatile int*>(&turn) = t + 1;
+    }
+}
+
+}  // namespace

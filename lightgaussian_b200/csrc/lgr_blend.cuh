@@ -112,8 +112,9 @@ __global__ void __launch_bounds__(BL_THREADS)
 blend_forward_ring_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H, int tiles_x,
                           const float2* __restrict__ means2D, const float4* __restrict__ conic_opacity, const float4* __restrict__ rgb,
                           const float* __restrict__ bg, float* __restrict__ final_T, uint32_t* __restrict__ n_contrib,
-                          float* __restrict__ out_color, int* __restrict__ count, float* __restrict__ rec_out)
+                          float* __restrict__ out_color, int* __restrict__ count, float* __restrict__ rec_out, const int* __restrict__ header)
 {
+    if (header[HDR_OVERFLOW]) return;   // the binning blob was too small for this view: the host repeats scatter + blend (lgr_bin.cuh)
     __shared__ __align__(128) BlendRing ring;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile = blockIdx.x;
@@ -315,7 +316,7 @@ __device__ __forceinline__ void back_flush(const BlendBackWarp& bw, int nbuf, in
 constexpr size_t blend_back_smem_bytes() { return sizeof(BlendRing) + 128 + 8 * sizeof(BlendBackWarp); }
 
 __global__ void __launch_bounds__(BL_THREADS)
-blend_backward_ring_kernel(const uint2* __restrict__ ranges, const char* __restrict__ binning_blob, const int* __restrict__ listed, int W, int H,
+blend_backward_ring_kernel(const uint2* __restrict__ ranges, const char* __restrict__ binning_blob, const int* __restrict__ header, int W, int H,
                            int tiles_x, const float* __restrict__ bg, const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib,
                            const float* __restrict__ dL_dpix, float* __restrict__ acc)
 {
@@ -344,8 +345,9 @@ blend_backward_ring_kernel(const uint2* __restrict__ ranges, const char* __restr
     if (warp == 8) {
         // ===== producer: one thread streams the records back to front with TMA bulk loads =====
         if (lane == 0) {
-            // records = second region of the binning blob (carve_binning): right behind the 4-byte ids of the `listed` instances
-            const size_t Rn = (size_t)max(listed[0], 1);
+            // records = second region of the binning blob (carve_binning): right behind the 4-byte ids of the instances the blob
+            // was sized for (header word HDR_CAPACITY, written on the device by the forward)
+            const size_t Rn = (size_t)max(header[HDR_CAPACITY], 1);
             const float* rec_in = reinterpret_cast<const float*>(binning_blob + (Rn * 4 + 255) / 256 * 256);
             for (uint32_t i = 0; i < nchunks; i++) {
                 const uint32_t b = nchunks - 1 - i;
@@ -374,10 +376,10 @@ blend_backward_ring_kernel(const uint2* __restrict__ ranges, const char* __restr
         d2 = dL_dpix[2 * plane + pix];
     }
     bw.d[lane] = make_float4(d0, d1, d2, 0.f);
-    const float bgT = -T_final * (bg[0] * d0 + bg[1] * d1 + bg[2] * d2);
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f;       // accum_rec
-    float lc0 = 0.f, lc1 = 0.f, lc2 = 0.f;    // last colour
-    float last_alpha = 0.f;
+    // D = sum_c dL/dpix_c * (background + everything blended BEHIND the current Gaussian), in absolute (not T-normalised) units:
+    // the reference's  T*(c - accum_rec).dpix - T_final/(1-alpha)*bg.dpix  (backward.cu:505-518) equals  T*(c.dpix) - D/(1-alpha),
+    // and D grows by alpha*T*(c.dpix) per blended Gaussian -- one scalar recurrence instead of three colour recurrences.
+    float D = T_final * (bg[0] * d0 + bg[1] * d1 + bg[2] * d2);
     int nbuf = 0;
     __syncwarp();
 
@@ -410,7 +412,7 @@ blend_backward_ring_kernel(const uint2* __restrict__ ranges, const char* __restr
                 float alpha = fminf(0.99f, q1.y * G);
                 const bool on = (b * BL_CH + (uint32_t)j < last) && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
                 if (!__any_sync(FULL, on)) continue;
-                // a lane that does not blend this Gaussian takes part as alpha = 0: T, the colour recurrence and both sums are unchanged
+                // a lane that does not blend this Gaussian takes part as alpha = 0: T, D and both sums are unchanged
                 G = on ? G : 0.f;
                 alpha = on ? alpha : 0.f;
                 const float one_m_a = 1.0f - alpha;   // in [0.01, 1]: MUFU.RCP + one Newton step is within 1 ulp
@@ -418,15 +420,11 @@ blend_backward_ring_kernel(const uint2* __restrict__ ranges, const char* __restr
                 asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rcp) : "f"(one_m_a));
                 rcp = fmaf(rcp, fmaf(-one_m_a, rcp, 1.0f), rcp);
                 T = T * rcp;
-                const float oml = 1.f - last_alpha;
-                a0 = fmaf(last_alpha, lc0, oml * a0);
-                a1 = fmaf(last_alpha, lc1, oml * a1);
-                a2 = fmaf(last_alpha, lc2, oml * a2);
-                lc0 = q1.z; lc1 = q1.w; lc2 = q2.x;
-                last_alpha = alpha;
-                float dL_dalpha = fmaf(q1.z - a0, d0, fmaf(q1.w - a1, d1, (q2.x - a2) * d2));
-                dL_dalpha = fmaf(dL_dalpha, T, bgT * rcp);
-                bw.w[nbuf][lane] = alpha * T;
+                const float cd = fmaf(q1.z, d0, fmaf(q1.w, d1, q2.x * d2));
+                const float dL_dalpha = fmaf(T, cd, -rcp * D);
+                const float w = alpha * T;
+                D = fmaf(w, cd, D);
+                bw.w[nbuf][lane] = w;
                 bw.g[nbuf][lane] = G * dL_dalpha;
                 if (lane == 0) {
                     bw.mid[nbuf] = q2.y;

@@ -164,11 +164,12 @@ __global__ void __launch_bounds__(256) preprocess_raw_kernel(RawArgs a, int* __r
 
     // everything that does not need the SH rows overlaps the copy
     if (valid) {
-        g.iota[i] = (uint32_t)i;
+        if (!g.bin_rec) g.iota[i] = (uint32_t)i;
         if (!visible) {
             radii[i] = 0;
             g.tiles_touched[i] = 0;
-            g.tiles_kept[i] = 0;
+            if (g.bin_rec) g.bin_rec[i] = make_uint4(0u, 0u, 0u, 0u);
+            else g.tiles_kept[i] = 0;
             g.depth_keys[i] = 0xffffffffu;
             g.clamped[i] = 0;
         } else {
@@ -183,8 +184,12 @@ __global__ void __launch_bounds__(256) preprocess_raw_kernel(RawArgs a, int* __r
             unsigned long long mask;
             uint32_t kept;
             tile_keep_mask(geo, co, a.W, a.H, mask, kept);
-            g.tiles_kept[i] = kept;
-            g.keep_mask[i] = mask;
+            if (g.bin_rec) {
+                g.bin_rec[i] = make_bin_rec(geo.rect.x0, geo.rect.y0, geo.rect.x1 - geo.rect.x0, geo.rect.y1 - geo.rect.y0, mask);
+            } else {
+                g.tiles_kept[i] = kept;
+                g.keep_mask[i] = mask;
+            }
         }
     }
     if (!any_vis) return;

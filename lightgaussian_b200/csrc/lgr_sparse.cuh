@@ -244,4 +244,149 @@ __global__ void __launch_bounds__(256) sparse_accumulate_kernel(SparseAccArgs a)
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Single-GPU K7+K8 on the compacted list (the dense kernel spends a full warp pass on every 32 Gaussians that hold even ONE
+// non-zero gradient -- 99 % of the warps at 13 % density -- and re-reads 0.7 GB of parameters for rows that come out as zeros).
+//
+//   kback_zero_flag_kernel    one pass over the 48-byte accumulator records: flags the Gaussians with a non-zero gradient, appends
+//                             their ids to a list (one atomicAdd per warp), and zero-fills EVERY dense output row of the block's 256
+//                             Gaussians with TMA bulk stores from one shared page of zeros (14 cp.async.bulk per block, issued by
+//                             one thread; no per-lane store instructions).
+//   preprocess_backward_compact_kernel   K7+K8 with the activation chain rules for the listed Gaussians only (all 32 lanes busy),
+//                             rows written over the zeros.  Grid-stride over the device-side count: no host synchronisation.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int KB_ZERO_BYTES = 5760;   // 32 rows x 45 floats: the dense dL/dfeatures_rest run of one warp at degree 3
+
+struct KbackZeroArgs {
+    int P, nrest;
+    const int* radii;
+    const float* acc;
+    int* idx;        // [P] out: ids with a non-zero gradient (unordered)
+    int* counter;    // out: how many
+    float* d_xyz; float* d_dc; float* d_rest; float* d_scaling; float* d_rotation; float* d_opacity; float* dL_dmeans2D;
+};
+
+__device__ __forceinline__ void bulk_zero(float* dst, size_t floats, const void* zero_page)
+{
+    size_t bytes = floats * 4;
+    char* p = reinterpret_cast<char*>(dst);
+    while (bytes) {
+        const uint32_t n = (uint32_t)(bytes < (size_t)KB_ZERO_BYTES ? bytes : (size_t)KB_ZERO_BYTES);
+        bulk_s2g(p, zero_page, n);
+        p += n;
+        bytes -= n;
+    }
+}
+
+__global__ void __launch_bounds__(256) kback_zero_flag_kernel(KbackZeroArgs a)
+{
+    __shared__ __align__(128) float zero_page[KB_ZERO_BYTES / 4];
+    for (int k = threadIdx.x; k < KB_ZERO_BYTES / 4; k += 256) zero_page[k] = 0.f;
+    fence_async_smem();
+    __syncthreads();
+    const int first = blockIdx.x * 256;
+    const int n = min(256, a.P - first);
+    if (threadIdx.x == 0) {
+        if (n == 256) {   // every run starts 16-byte aligned and is a multiple of 16 bytes
+            bulk_zero(a.d_rest + (size_t)first * a.nrest, (size_t)256 * a.nrest, zero_page);
+            bulk_zero(a.d_dc + (size_t)first * 3, 768, zero_page);
+            bulk_zero(a.d_xyz + (size_t)first * 3, 768, zero_page);
+            bulk_zero(a.d_scaling + (size_t)first * 3, 768, zero_page);
+            bulk_zero(a.d_rotation + (size_t)first * 4, 1024, zero_page);
+            bulk_zero(a.d_opacity + (size_t)first, 256, zero_page);
+            bulk_zero(a.dL_dmeans2D + (size_t)first * 3, 768, zero_page);
+            bulk_commit();
+        }
+    }
+    if (n < 256) {   // ragged last block: plain stores
+        for (int k = threadIdx.x; k < n * a.nrest; k += 256) a.d_rest[(size_t)first * a.nrest + k] = 0.f;
+        for (int k = threadIdx.x; k < n * 3; k += 256) {
+            a.d_dc[(size_t)first * 3 + k] = 0.f; a.d_xyz[(size_t)first * 3 + k] = 0.f; a.d_scaling[(size_t)first * 3 + k] = 0.f;
+            a.dL_dmeans2D[(size_t)first * 3 + k] = 0.f;
+        }
+        for (int k = threadIdx.x; k < n * 4; k += 256) a.d_rotation[(size_t)first * 4 + k] = 0.f;
+        for (int k = threadIdx.x; k < n; k += 256) a.d_opacity[(size_t)first + k] = 0.f;
+    }
+    const int i = first + threadIdx.x;
+    bool nz = false;
+    if (i < a.P && a.radii[i] > 0) {
+        const float4* r = reinterpret_cast<const float4*>(a.acc + (size_t)i * ACC_STRIDE);
+        const float4 u = r[0], w = r[1];
+        const float c = a.acc[(size_t)i * ACC_STRIDE + 8];
+        nz = u.x != 0.f || u.y != 0.f || u.z != 0.f || u.w != 0.f || w.x != 0.f || w.y != 0.f || w.z != 0.f || w.w != 0.f || c != 0.f;
+    }
+    const unsigned word = __ballot_sync(FULL, nz);
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == 0 && word) base = atomicAdd(a.counter, __popc(word));
+    base = __shfl_sync(FULL, base, 0);
+    if (nz) a.idx[base + __popc(word & ((1u << lane) - 1u))] = i;
+    if (threadIdx.x == 0 && n == 256) bulk_wait_read_all();   // the zero page must outlive the copies that read it
+}
+
+__global__ void __launch_bounds__(256) preprocess_backward_compact_kernel(RawBackArgs a, const int* __restrict__ idx, const int* __restrict__ counter)
+{
+    __shared__ float s_cam[36];
+    if (threadIdx.x < 16) s_cam[threadIdx.x] = a.view[threadIdx.x];
+    else if (threadIdx.x < 32) s_cam[threadIdx.x] = a.proj[threadIdx.x - 16];
+    else if (threadIdx.x < 35) s_cam[threadIdx.x] = a.campos[threadIdx.x - 32];
+    __syncthreads();
+    const float* view = s_cam;
+    const float* proj = s_cam + 16;
+    const float* cam = s_cam + 32;
+    const int count = *counter;
+    const int nrest = (a.M - 1) * 3;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < count; t += gridDim.x * blockDim.x) {
+        const int i = idx[t];
+        const size_t si = (size_t)i;
+        float dmean[3] = {0.f, 0.f, 0.f}, dscale[3], dq[4], dRGB[3];
+        const float4 co = a.conic_opacity[si];
+        const Grad2D g2 = accum_to_grad2d(a.acc + si * ACC_STRIDE, co, a.W, a.H);
+        const float x = a.xyz[3 * si], y = a.xyz[3 * si + 1], z = a.xyz[3 * si + 2];
+        float c3[6], dcov[6];
+#pragma unroll
+        for (int k = 0; k < 6; k++) c3[k] = a.cov3D[6 * si + k];
+        lgr::cov2d_backward(x, y, z, view, c3, a.fx, a.fy, a.tanx, a.tany, g2.dcx, g2.dcy, g2.dcw, dcov, dmean);
+        lgr::mean2d_backward(x, y, z, proj, g2.dm2x, g2.dm2y, dmean);
+        const unsigned cb = a.clamped[i];
+        dRGB[0] = (cb & 1u) ? 0.f : g2.dcol[0]; dRGB[1] = (cb & 2u) ? 0.f : g2.dcol[1]; dRGB[2] = (cb & 4u) ? 0.f : g2.dcol[2];
+        const float s0 = act_exp(a.scaling[3 * si]), s1 = act_exp(a.scaling[3 * si + 1]), s2 = act_exp(a.scaling[3 * si + 2]);
+        float dn;
+        const float4 v = reinterpret_cast<const float4*>(a.rotation)[si];
+        const float4 q = act_normalize(v, dn);
+        float ds[3], dqn[4];
+        lgr::cov3d_backward(s0, s1, s2, a.mod, q.x, q.y, q.z, q.w, dcov, ds, dqn);
+        dscale[0] = ds[0] * s0; dscale[1] = ds[1] * s1; dscale[2] = ds[2] * s2;
+        const float qg = q.x * dqn[0] + q.y * dqn[1] + q.z * dqn[2] + q.w * dqn[3];
+        const float inv = 1.0f / dn;
+        dq[0] = (dqn[0] - q.x * qg) * inv; dq[1] = (dqn[1] - q.y * qg) * inv;
+        dq[2] = (dqn[2] - q.z * qg) * inv; dq[3] = (dqn[3] - q.w * qg) * inv;
+        const float o = co.w;
+        const float dop = (g2.dop * (1.0f - o)) * o;
+        float* grow = a.d_rest + si * nrest;
+        float* gdc = a.d_dc + si * 3;
+        if (a.D > 0) {
+            const float* rr = a.rest + si * a.rest_stride;
+            const float* dd = a.dc + si * 3;
+            lgr::sh_backward(a.D, [&](int k) { return k < 3 ? __ldg(dd + k) : __ldg(rr + k - 3); },
+                             [&](int k, int c, float val) {
+                                 if (k == 0) gdc[c] = val;
+                                 else grow[3 * (k - 1) + c] = val;
+                             },
+                             x, y, z, cam, dRGB, dmean);
+        } else {
+#pragma unroll
+            for (int c = 0; c < 3; c++) gdc[c] = LGR_C0 * dRGB[c];
+        }
+        a.d_xyz[3 * si] = dmean[0]; a.d_xyz[3 * si + 1] = dmean[1]; a.d_xyz[3 * si + 2] = dmean[2];
+        a.d_scaling[3 * si] = dscale[0]; a.d_scaling[3 * si + 1] = dscale[1]; a.d_scaling[3 * si + 2] = dscale[2];
+        reinterpret_cast<float4*>(a.d_rotation)[si] = make_float4(dq[0], dq[1], dq[2], dq[3]);
+        a.d_opacity[si] = dop;
+        a.dL_dmeans2D[3 * si] = g2.dm2x; a.dL_dmeans2D[3 * si + 1] = g2.dm2y;
+        if (a.d_rgb) {
+            a.d_rgb[3 * si] = dRGB[0]; a.d_rgb[3 * si + 1] = dRGB[1]; a.d_rgb[3 * si + 2] = dRGB[2];
+        }
+    }
+}
+
 }  // namespace

@@ -44,17 +44,23 @@ constexpr int ACC_STRIDE = 12;  // floats per Gaussian in the backward accumulat
 
 thread_local std::string g_last_error;
 int g_blend_mode = 0;   // 0 = ring kernels (lgr_blend.cuh), 1 = round-1 kernels (kept for A/B measurements and as a cross-check in the tests)
+// binning (lgr_bin.cuh): 0 = hand-written kernels, binning blob sized from a running estimate, no GPU idle on the host (default);
+// 1 = hand-written kernels, blob sized exactly after a stream synchronisation; 2 = round-1 path (library radix sorts + scan, host sync)
+int g_bin_mode = 0;
+int g_kback_mode = 0;   // single-GPU fused K7+K8: 0 = zero-fill + compacted list (lgr_sparse.cuh), 1 = dense kernel (A/B)
+std::atomic<size_t> g_bin_hint{0};   // running estimate of the listed instances per view (mode 0)
 std::atomic<uint64_t> g_launches{0};
 
 // ---- optional per-stage device timing (CUDA events on the launch stream), used by bench.py's roofline ----
 enum StageId { ST_PREPROCESS = 0, ST_DEPTH_SORT, ST_SCAN, ST_EMIT, ST_TILE_SORT, ST_RANGES, ST_BLEND_FWD, ST_BLEND_FWD_COUNT,
-               ST_SCORE, ST_BLEND_BWD, ST_PREPROCESS_BWD, ST_MEMSET, ST_SH_GRAD, ST_PEER_ALLREDUCE, ST_LOSS_FWD, ST_LOSS_BWD, ST_ADAMW, ST_COMPACT, ST_VQ_ASSIGN, ST_VQ_UPDATE, ST_SPARSE_PACK, ST_SPARSE_ACC, ST_COUNT };
+               ST_SCORE, ST_BLEND_BWD, ST_PREPROCESS_BWD, ST_MEMSET, ST_SH_GRAD, ST_PEER_ALLREDUCE, ST_LOSS_FWD, ST_LOSS_BWD, ST_ADAMW, ST_COMPACT, ST_VQ_ASSIGN, ST_VQ_UPDATE, ST_SPARSE_PACK, ST_SPARSE_ACC, ST_BIN_DSORT, ST_BIN_COUNT, ST_BIN_SCATTER, ST_COUNT };
 const char* const kStageNames[ST_COUNT] = {"preprocess_kernel", "depth_sort(cub)", "scan(cub)", "emit_kernel", "tile_sort(cub)",
                                            "ranges_kernel", "blend_forward_kernel", "blend_forward_kernel<count>", "score_kernel",
                                            "blend_backward_kernel", "preprocess_backward_kernel", "memset", "sh_grad_from_views_kernel",
                                            "peer_allreduce_kernel", "image_loss_forward_kernel", "image_loss_backward_kernel", "adamw_multi_kernel",
                                            "compact_gather_kernel", "vq_assign_kernel", "vq_ema_kernels", "sparse_pack(flag+scan+index+K8)",
-                                           "sparse_accumulate_kernel"};
+                                           "sparse_accumulate_kernel", "depth_sort(dsort_count+bin_scan+dsort_scatter x3)", "tile_count_kernel+bin_scan_kernel",
+                                           "tile_scatter_kernel"};
 struct ProfRecord { int stage; cudaEvent_t a, b; };
 bool g_prof_on = false;
 std::vector<ProfRecord> g_prof_records;
@@ -104,6 +110,10 @@ struct ProfScope {
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+}  // namespace
+#include "lgr_bin.cuh"
+namespace {
+
 // Sub-allocation of one opaque blob (the role of obtain()/required() in
 // RAST/cuda_rasterizer/rasterizer_impl.h:21-73).  With base == nullptr it only measures.
 struct Carver {
@@ -129,15 +139,20 @@ struct GeometryState {
     float* cov3D;              // [6P]
     uint8_t* clamped;          // [P] bit c = channel c clamped
     uint32_t* tiles_touched;   // [P] tile-rectangle area (the reference's definition)
+    uint32_t* sorted_ids;      // [P] Gaussian ids in (depth bits, id) order; culled ones last
+    float* grad_acc;           // [12P] backward accumulator records
+    // forward-only binning scratch.  Hand-written binning (g_bin_mode 0/1): aliased INSIDE the grad_acc region (dead before the
+    // backward clears it): bin_rec, depth_keys, depth_keys_sorted, iota (= second id buffer of the depth sort).
+    uint4* bin_rec;            // [P] tile rectangle + exact 64-bit keep mask (lgr_bin.cuh); NULL on the library path
+    uint32_t* depth_keys;      // [P]
+    uint32_t* depth_keys_sorted;  // [P]
+    uint32_t* iota;            // [P]
+    // library path only (g_bin_mode 2), behind grad_acc
     uint32_t* tiles_kept;      // [P] instances actually emitted after exact tile culling (<= tiles_touched)
     unsigned long long* keep_mask;  // [P] bit b set = rectangle tile b (row-major) is kept; all ones when the rectangle has > 64 tiles
-    uint32_t* sorted_ids;      // [P] Gaussian ids in (depth bits, id) order; culled ones last
-    uint32_t* depth_keys;      // [P] scratch
-    uint32_t* depth_keys_sorted;  // [P] scratch
-    uint32_t* iota;            // [P] scratch
     unsigned long long* offsets;  // [P] inclusive scan in sorted order: low word kept instances, high word rectangle areas
-    float* grad_acc;           // [12P] backward accumulator records
-    int* num_rendered;         // header: [0] instances emitted (kept), [1] sum of tiles_touched (the reference's num_rendered)
+    int* num_rendered;         // header (64 ints): [0] instances listed, [1] the reference's num_rendered (sum of tiles_touched),
+                               //   [2] capacity of the binning blob, [3] capacity overflow flag, [8] scan kernels' arrival counter
     char* cub_temp;
     size_t cub_temp_bytes;
     size_t offs[8];
@@ -155,7 +170,8 @@ struct TilesTouchedOp {
     }
 };
 
-GeometryState carve_geometry(char* base, size_t P)
+// The part the backward reads (everything up to and including grad_acc) has the same layout in every binning mode.
+GeometryState carve_geometry(char* base, size_t P, bool library_binning)
 {
     GeometryState g;
     Carver c(base);
@@ -168,20 +184,34 @@ GeometryState carve_geometry(char* base, size_t P)
     g.clamped = c.take<uint8_t>(P, &g.offs[5]);
     g.tiles_touched = c.take<uint32_t>(P, &g.offs[6]);
     g.sorted_ids = c.take<uint32_t>(P, &g.offs[7]);
-    g.tiles_kept = c.take<uint32_t>(P);
-    g.keep_mask = c.take<unsigned long long>(P);
-    g.depth_keys = c.take<uint32_t>(P);
-    g.depth_keys_sorted = c.take<uint32_t>(P);
-    g.iota = c.take<uint32_t>(P);
-    g.offsets = c.take<unsigned long long>(P);
-    g.grad_acc = c.take<float>(ACC_STRIDE * P);
-    size_t sort_bytes = 0, scan_bytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr,
-                                    (uint32_t*)nullptr, (int)P, 0, 32);
-    auto it = thrust::make_transform_iterator((const uint32_t*)nullptr, TilesTouchedOp{nullptr, nullptr});
-    cub::DeviceScan::InclusiveSum(nullptr, scan_bytes, it, (unsigned long long*)nullptr, (int)P);
-    g.cub_temp_bytes = sort_bytes > scan_bytes ? sort_bytes : scan_bytes;
-    g.cub_temp = c.take<char>(g.cub_temp_bytes);
+    const size_t acc_bytes = sizeof(float) * ACC_STRIDE * P, scratch_bytes = 28 * P + 4 * 256;
+    size_t acc_off = 0;
+    char* region = c.take<char>(std::max(acc_bytes, scratch_bytes), &acc_off);
+    g.grad_acc = reinterpret_cast<float*>(region);
+    g.bin_rec = nullptr;
+    g.tiles_kept = nullptr; g.keep_mask = nullptr; g.offsets = nullptr;
+    g.cub_temp = nullptr; g.cub_temp_bytes = 0;
+    if (!library_binning) {
+        Carver a(region);   // aliases grad_acc
+        g.bin_rec = a.take<uint4>(P);
+        g.depth_keys = a.take<uint32_t>(P);
+        g.depth_keys_sorted = a.take<uint32_t>(P);
+        g.iota = a.take<uint32_t>(P);
+    } else {
+        g.tiles_kept = c.take<uint32_t>(P);
+        g.keep_mask = c.take<unsigned long long>(P);
+        g.depth_keys = c.take<uint32_t>(P);
+        g.depth_keys_sorted = c.take<uint32_t>(P);
+        g.iota = c.take<uint32_t>(P);
+        g.offsets = c.take<unsigned long long>(P);
+        size_t sort_bytes = 0, scan_bytes = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr,
+                                        (uint32_t*)nullptr, (int)P, 0, 32);
+        auto it = thrust::make_transform_iterator((const uint32_t*)nullptr, TilesTouchedOp{nullptr, nullptr});
+        cub::DeviceScan::InclusiveSum(nullptr, scan_bytes, it, (unsigned long long*)nullptr, (int)P);
+        g.cub_temp_bytes = sort_bytes > scan_bytes ? sort_bytes : scan_bytes;
+        g.cub_temp = c.take<char>(g.cub_temp_bytes);
+    }
     g.total = align_up(c.off, 256);
     return g;
 }
@@ -190,11 +220,16 @@ struct ImageState {
     float* final_T;       // [N]
     uint32_t* n_contrib;  // [N]
     uint2* ranges;        // [tiles]
+    // forward-only scratch of the hand-written binning (lgr_bin.cuh); NULL on the library path
+    uint32_t* bin_M;      // [BIN_V][max(DS_BINS, tiles_pad)] count matrix
+    uint32_t* bin_total;  // [max(DS_BINS, tiles_pad)]
+    uint32_t* bin_base;   // [max(DS_BINS, tiles_pad)]
     size_t offs[3];
     size_t total;
 };
 
-ImageState carve_image(char* base, int W, int H)
+// the part the backward reads (final_T, n_contrib, ranges) has the same layout in every binning mode
+ImageState carve_image(char* base, int W, int H, bool library_binning)
 {
     ImageState s;
     const size_t N = (size_t)W * H;
@@ -203,6 +238,13 @@ ImageState carve_image(char* base, int W, int H)
     s.final_T = c.take<float>(N, &s.offs[0]);
     s.n_contrib = c.take<uint32_t>(N, &s.offs[1]);
     s.ranges = c.take<uint2>(tiles, &s.offs[2]);
+    s.bin_M = s.bin_total = s.bin_base = nullptr;
+    if (!library_binning) {
+        const size_t pad = std::max((size_t)DS_BINS, (size_t)bin_pad((int)tiles));
+        s.bin_M = c.take<uint32_t>((size_t)BIN_V * pad);
+        s.bin_total = c.take<uint32_t>(pad);
+        s.bin_base = c.take<uint32_t>(pad);
+    }
     s.total = align_up(c.off, 256);
     return s;
 }
@@ -228,7 +270,8 @@ struct BinningState {
     size_t total;
 };
 
-BinningState carve_binning(char* base, size_t R, int W, int H)
+// R = instances the blob holds: the listed count on the library path and in mode 1, the capacity estimate in mode 0
+BinningState carve_binning(char* base, size_t R, int W, int H, bool library_binning)
 {
     BinningState b;
     const int bits = tile_key_bits(W, H);
@@ -237,6 +280,11 @@ BinningState carve_binning(char* base, size_t R, int W, int H)
     Carver c(base);
     b.point_list = c.take<uint32_t>(Rn, &b.offs[0]);
     b.records = c.take<float>(Rn * 12);   // second region: its offset, align_up(4*max(R,1), 256), is recomputed ON THE DEVICE by the backward
+    b.ids_unsorted = nullptr; b.keys_unsorted = b.keys_sorted = nullptr; b.cub_temp = nullptr; b.cub_temp_bytes = 0;
+    if (!library_binning) {
+        b.total = align_up(c.off, 256);
+        return b;
+    }
     b.ids_unsorted = c.take<uint32_t>(Rn);
     const size_t ksz = b.wide_keys ? 4 : 2;
     b.keys_unsorted = c.take<char>(Rn * ksz);
@@ -293,7 +341,9 @@ __device__ __forceinline__ void tile_keep_mask(const lgr::Geom& geo, float4 co, 
     const int area = w * h;
     mask = ~0ull;
     kept = (uint32_t)area;
-    if (area > 64 || !g_tile_cull_enabled) return;
+    if (area > 64) return;
+    if (area < 64) mask = (1ull << area) - 1ull;   // bits >= area stay clear: popcount(mask) = instances listed
+    if (!g_tile_cull_enabled) return;
     // same test as subtile_cull(), with everything that does not depend on the tile hoisted out of the loop
     const float A = co.x, B = co.y, Cc = co.z;
     const float t = 257.55f * co.w;
@@ -385,7 +435,7 @@ __global__ void __launch_bounds__(256) preprocess_kernel(PreprocessArgs a, int* 
         printf("Point is filtered although prefiltered is set. This shouldn't happen!");
         __trap();
     }
-    g.iota[i] = (uint32_t)i;
+    if (!g.bin_rec) g.iota[i] = (uint32_t)i;
     if (have_cov) {  // the reference stores cov3D before the later culls (forward.cu:213)
 #pragma unroll
         for (int k = 0; k < 6; k++) g.cov3D[6 * (size_t)i + k] = cov[k];
@@ -393,7 +443,8 @@ __global__ void __launch_bounds__(256) preprocess_kernel(PreprocessArgs a, int* 
     if (!visible) {
         radii[i] = 0;
         g.tiles_touched[i] = 0;
-        g.tiles_kept[i] = 0;
+        if (g.bin_rec) g.bin_rec[i] = make_uint4(0u, 0u, 0u, 0u);
+        else g.tiles_kept[i] = 0;
         g.depth_keys[i] = 0xffffffffu;
         g.clamped[i] = 0;
         return;
@@ -433,8 +484,12 @@ __global__ void __launch_bounds__(256) preprocess_kernel(PreprocessArgs a, int* 
     unsigned long long mask;
     uint32_t kept;
     tile_keep_mask(geo, make_float4(geo.conic_x, geo.conic_y, geo.conic_z, a.opacities[i]), a.W, a.H, mask, kept);
-    g.tiles_kept[i] = kept;
-    g.keep_mask[i] = mask;
+    if (g.bin_rec) {
+        g.bin_rec[i] = make_bin_rec(geo.rect.x0, geo.rect.y0, geo.rect.x1 - geo.rect.x0, geo.rect.y1 - geo.rect.y0, mask);
+    } else {
+        g.tiles_kept[i] = kept;
+        g.keep_mask[i] = mask;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -536,8 +591,9 @@ __global__ void __launch_bounds__(256)
 blend_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list, int W, int H, int tiles_x,
                      const float2* __restrict__ means2D, const float4* __restrict__ conic_opacity, const float4* __restrict__ rgb,
                      const float* __restrict__ bg, float* __restrict__ final_T, uint32_t* __restrict__ n_contrib,
-                     float* __restrict__ out_color, int* __restrict__ count)
+                     float* __restrict__ out_color, int* __restrict__ count, const int* __restrict__ header)
 {
+    if (header[HDR_OVERFLOW]) return;   // binning blob too small: the host repeats scatter + blend (lgr_bin.cuh)
     __shared__ float2 s_xy[8][32];
     __shared__ float4 s_co[8][32];
     __shared__ float4 s_rgb[8][32];
@@ -950,6 +1006,26 @@ struct PinnedInt {
 };
 thread_local PinnedInt t_pinned;
 
+struct SyncEvent {
+    cudaEvent_t e = nullptr;
+    ~SyncEvent() { if (e) cudaEventDestroy(e); }
+    cudaEvent_t get()
+    {
+        if (!e) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+        return e;
+    }
+};
+thread_local SyncEvent t_event;
+std::atomic<uint64_t> g_bin_overflows{0};
+
+__global__ void set_capacity_kernel(int* header, int capacity)
+{
+    if (threadIdx.x == 0) {
+        header[HDR_CAPACITY] = capacity;
+        header[HDR_OVERFLOW] = 0;
+    }
+}
+
 int forward_impl(const lgr_view* v, int P, int M, const float* means3D, const float* shs, const float* colors_precomp,
                  const float* opacities, const float* scales, const float* rotations, const float* cov3D_precomp,
                  lgr_alloc_fn geometry_alloc, void* geometry_user, lgr_alloc_fn binning_alloc, void* binning_user,
@@ -1012,20 +1088,19 @@ int forward_impl(const lgr_view* v, int P, int M, const float* means3D, const fl
         g_last_error = "lgr_forward: rotations and shs must be 16-byte aligned";
         return LGR_ERR_INVALID_ARG;
     }
-    GeometryState geo = carve_geometry(nullptr, (size_t)P);
+    const int tiles = gx * gy;
+    const bool lib_bin = g_bin_mode == 2 || tiles > BIN_MAX_TILES || gx > 0xffff || gy > 0xffff;
+    GeometryState geo = carve_geometry(nullptr, (size_t)P, lib_bin);
     char* geo_blob = geometry_alloc(geometry_user, geo.total);
     if (!geo_blob) { g_last_error = "geometry allocator returned NULL"; return LGR_ERR_ALLOC; }
-    geo = carve_geometry(geo_blob, (size_t)P);
+    geo = carve_geometry(geo_blob, (size_t)P, lib_bin);
 
-    ImageState img = carve_image(nullptr, W, H);
+    ImageState img = carve_image(nullptr, W, H, lib_bin);
     char* img_blob = image_alloc(image_user, img.total);
     if (!img_blob) { g_last_error = "image allocator returned NULL"; return LGR_ERR_ALLOC; }
-    img = carve_image(img_blob, W, H);
-    LGR_CUDA_TRY(cudaMemsetAsync(img.ranges, 0, sizeof(uint2) * (size_t)gx * gy, stream));
+    img = carve_image(img_blob, W, H, lib_bin);
 
-    int R = 0, R_ref = 0;
-    BinningState bin;
-    if (P > 0) {
+    {
         PreprocessArgs a;
         a.P = P; a.D = v->sh_degree; a.M = M; a.W = W; a.H = H; a.gx = gx; a.gy = gy;
         a.fy = H / (2.0f * v->tan_fovy);   // rasterizer_impl.cu:223-224
@@ -1052,89 +1127,199 @@ int forward_impl(const lgr_view* v, int P, int M, const float* means3D, const fl
             preprocess_kernel<<<blocks, 256, 0, stream>>>(a, radii, geo);
         }
         LGR_LAUNCH_CHECK("preprocess_kernel", debug, stream);
+    }
 
+    int R = 0, R_ref = 0;
+    BinningState bin = {};
+    int* host_hdr = t_pinned.get();
+
+    // K4/K5 -- and everything of it that has to be repeated when the binning blob turns out too small
+    auto launch_blend = [&]() -> int {
+        if (count_mode) LGR_CUDA_TRY(cudaMemsetAsync(gaussians_count, 0, sizeof(int) * (size_t)P, stream));
+        ProfScope ps(count_mode ? ST_BLEND_FWD_COUNT : ST_BLEND_FWD, stream);
+        if (g_blend_mode == 0 && count_mode)
+            blend_forward_ring_kernel<true, false><<<tiles, BL_THREADS, 0, stream>>>(img.ranges, bin.point_list, W, H, gx, geo.means2D, geo.conic_opacity,
+                                                                                      geo.rgb, v->background, img.final_T, img.n_contrib, out_color,
+                                                                                      gaussians_count, nullptr, geo.num_rendered);
+        else if (g_blend_mode == 0)
+            blend_forward_ring_kernel<false, true><<<tiles, BL_THREADS, 0, stream>>>(img.ranges, bin.point_list, W, H, gx, geo.means2D, geo.conic_opacity,
+                                                                                      geo.rgb, v->background, img.final_T, img.n_contrib, out_color,
+                                                                                      nullptr, bin.records, geo.num_rendered);
+        else if (count_mode)
+            blend_forward_kernel<true><<<tiles, 256, 0, stream>>>(img.ranges, bin.point_list, W, H, gx, geo.means2D, geo.conic_opacity,
+                                                                   geo.rgb, v->background, img.final_T, img.n_contrib, out_color,
+                                                                   gaussians_count, geo.num_rendered);
+        else
+            blend_forward_kernel<false><<<tiles, 256, 0, stream>>>(img.ranges, bin.point_list, W, H, gx, geo.means2D, geo.conic_opacity,
+                                                                    geo.rgb, v->background, img.final_T, img.n_contrib, out_color,
+                                                                    nullptr, geo.num_rendered);
+        LGR_LAUNCH_CHECK("blend_forward_kernel", debug, stream);
+        return LGR_OK;
+    };
+
+    if (!lib_bin) {
+        // ---------------- hand-written binning (lgr_bin.cuh) ----------------
+        const int per_block = bin_per_block(P);
+        const int tiles_pad = bin_pad(tiles);
+        {
+            ProfScope ps(ST_BIN_DSORT, stream);
+            BinScanArgs sa;
+            sa.M = img.bin_M; sa.V = BIN_V; sa.bins = DS_BINS; sa.bins_pad = DS_BINS; sa.bin_total = img.bin_total; sa.bin_base = img.bin_base;
+            sa.header = geo.num_rendered; sa.ranges = nullptr; sa.capacity = 0;
+            // 11 + 11 + 10 bits: depth_keys -> (depth_keys_sorted, sorted_ids) -> (depth_keys, iota) -> sorted_ids
+            dsort_count_kernel<0, true><<<BIN_V, 256, 0, stream>>>(geo.depth_keys, P, per_block, img.bin_M, geo.num_rendered);
+            bin_scan_kernel<false><<<DS_BINS / 32, 256, 0, stream>>>(sa);
+            dsort_scatter_kernel<0, true, false><<<BIN_V, 256, 0, stream>>>(geo.depth_keys, nullptr, geo.depth_keys_sorted, geo.sorted_ids, img.bin_M,
+                                                                           img.bin_base, P, per_block);
+            dsort_count_kernel<DS_BITS, false><<<BIN_V, 256, 0, stream>>>(geo.depth_keys_sorted, P, per_block, img.bin_M, geo.num_rendered);
+            bin_scan_kernel<false><<<DS_BINS / 32, 256, 0, stream>>>(sa);
+            dsort_scatter_kernel<DS_BITS, false, false><<<BIN_V, 256, 0, stream>>>(geo.depth_keys_sorted, geo.sorted_ids, geo.depth_keys, geo.iota,
+                                                                                  img.bin_M, img.bin_base, P, per_block);
+            dsort_count_kernel<2 * DS_BITS, false><<<BIN_V, 256, 0, stream>>>(geo.depth_keys, P, per_block, img.bin_M, geo.num_rendered);
+            bin_scan_kernel<false><<<DS_BINS / 32, 256, 0, stream>>>(sa);
+            dsort_scatter_kernel<2 * DS_BITS, false, true><<<BIN_V, 256, 0, stream>>>(geo.depth_keys, geo.iota, nullptr, geo.sorted_ids, img.bin_M,
+                                                                                      img.bin_base, P, per_block);
+            g_launches.fetch_add(8, std::memory_order_relaxed);
+            LGR_LAUNCH_CHECK("depth sort kernels", debug, stream);
+        }
+        const size_t tb_smem = sizeof(uint32_t) * (size_t)tiles_pad;
+        if (tb_smem > 48 * 1024) {
+            LGR_CUDA_TRY(cudaFuncSetAttribute(tile_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tb_smem));
+            LGR_CUDA_TRY(cudaFuncSetAttribute(tile_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tb_smem));
+        }
+        const bool exact = g_bin_mode == 1;
+        size_t capacity = 0;
+        if (!exact) {   // size the blob now, from the running estimate
+            capacity = std::max(g_bin_hint.load(std::memory_order_relaxed), (size_t)4096);
+            bin = carve_binning(nullptr, capacity, W, H, false);
+            char* bin_blob = binning_alloc(binning_user, bin.total);
+            if (!bin_blob) { g_last_error = "binning allocator returned NULL"; return LGR_ERR_ALLOC; }
+            bin = carve_binning(bin_blob, capacity, W, H, false);
+        }
+        {
+            ProfScope ps(ST_BIN_COUNT, stream);
+            tile_count_kernel<<<BIN_V, TB_THREADS, tb_smem, stream>>>(geo.sorted_ids, geo.bin_rec, P, per_block, gx, tiles_pad, img.bin_M, geo.num_rendered);
+            BinScanArgs sa;
+            sa.M = img.bin_M; sa.V = BIN_V; sa.bins = tiles; sa.bins_pad = tiles_pad; sa.bin_total = img.bin_total; sa.bin_base = img.bin_base;
+            sa.header = geo.num_rendered; sa.ranges = img.ranges;
+            sa.capacity = exact ? 0xffffffffu : (uint32_t)std::min(capacity, (size_t)0x7fffffff);
+            bin_scan_kernel<true><<<tiles_pad / 32, 256, 0, stream>>>(sa);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            LGR_LAUNCH_CHECK("tile_count_kernel", debug, stream);
+        }
+        LGR_CUDA_TRY(cudaMemcpyAsync(host_hdr, geo.num_rendered, 4 * sizeof(int), cudaMemcpyDeviceToHost, stream));
+        auto launch_scatter = [&]() -> int {
+            ProfScope ps(ST_BIN_SCATTER, stream);
+            tile_scatter_kernel<<<BIN_V, TB_THREADS, tb_smem, stream>>>(geo.sorted_ids, geo.bin_rec, P, per_block, gx, tiles_pad, img.bin_M, img.bin_base,
+                                                                        geo.num_rendered, bin.point_list);
+            LGR_LAUNCH_CHECK("tile_scatter_kernel", debug, stream);
+            return LGR_OK;
+        };
+        auto exact_blob = [&]() -> int {   // (re)allocate for exactly R instances and tell the device
+            bin = carve_binning(nullptr, (size_t)R, W, H, false);
+            char* bin_blob = binning_alloc(binning_user, bin.total);
+            if (!bin_blob) { g_last_error = "binning allocator returned NULL"; return LGR_ERR_ALLOC; }
+            bin = carve_binning(bin_blob, (size_t)R, W, H, false);
+            set_capacity_kernel<<<1, 32, 0, stream>>>(geo.num_rendered, R > 0 ? R : 1);
+            LGR_LAUNCH_CHECK("set_capacity_kernel", debug, stream);
+            return LGR_OK;
+        };
+        if (exact) {
+            LGR_CUDA_TRY(cudaStreamSynchronize(stream));
+            R = host_hdr[HDR_LISTED];
+            R_ref = host_hdr[HDR_RENDERED];
+            int st = exact_blob();
+            if (st != LGR_OK) return st;
+            if ((st = launch_scatter()) != LGR_OK) return st;
+            if ((st = launch_blend()) != LGR_OK) return st;
+        } else {
+            // the count is on its way to the host; scatter and blend are queued behind it right away, so the GPU keeps working while the
+            // host waits for those 16 bytes
+            cudaEvent_t ev = t_event.get();
+            LGR_CUDA_TRY(cudaEventRecord(ev, stream));
+            int st = launch_scatter();
+            if (st != LGR_OK) return st;
+            if ((st = launch_blend()) != LGR_OK) return st;
+            LGR_CUDA_TRY(cudaEventSynchronize(ev));
+            R = host_hdr[HDR_LISTED];
+            R_ref = host_hdr[HDR_RENDERED];
+            if ((size_t)R > capacity) {   // estimate too small (first view, or a jump between views): both kernels returned early; repeat
+                if ((st = exact_blob()) != LGR_OK) return st;
+                if ((st = launch_scatter()) != LGR_OK) return st;
+                if ((st = launch_blend()) != LGR_OK) return st;
+                g_bin_overflows.fetch_add(1, std::memory_order_relaxed);
+            }
+            // next estimate: 25 % above this view, never dropping by more than 2 % per view
+            const size_t want = (size_t)R + (size_t)R / 4 + 4096, keep = g_bin_hint.load(std::memory_order_relaxed) / 50 * 49;
+            g_bin_hint.store(std::max(want, keep), std::memory_order_relaxed);
+        }
+    } else {
+        // ---------------- round-1 path: library radix sorts and scan ----------------
+        LGR_CUDA_TRY(cudaMemsetAsync(geo.num_rendered, 0, 64 * sizeof(int), stream));
+        LGR_CUDA_TRY(cudaMemsetAsync(img.ranges, 0, sizeof(uint2) * (size_t)gx * gy, stream));
         size_t tmp = geo.cub_temp_bytes;
         {
             ProfScope ps(ST_DEPTH_SORT, stream);
             LGR_CUDA_TRY(cub::DeviceRadixSort::SortPairs(geo.cub_temp, tmp, (const uint32_t*)geo.depth_keys, geo.depth_keys_sorted,
                                                           (const uint32_t*)geo.iota, geo.sorted_ids, P, 0, 32, stream));
         }
-            auto it = thrust::make_transform_iterator((const uint32_t*)geo.sorted_ids, TilesTouchedOp{geo.tiles_kept, geo.tiles_touched});
+        auto it = thrust::make_transform_iterator((const uint32_t*)geo.sorted_ids, TilesTouchedOp{geo.tiles_kept, geo.tiles_touched});
         tmp = geo.cub_temp_bytes;
         {
             ProfScope ps(ST_SCAN, stream);
             LGR_CUDA_TRY(cub::DeviceScan::InclusiveSum(geo.cub_temp, tmp, it, geo.offsets, P, stream));
         }
-        int* host_R = t_pinned.get();
         LGR_CUDA_TRY(cudaMemcpyAsync(geo.num_rendered, geo.offsets + (P - 1), 2 * sizeof(int), cudaMemcpyDeviceToDevice, stream));
-        LGR_CUDA_TRY(cudaMemcpyAsync(host_R, geo.offsets + (P - 1), 2 * sizeof(int), cudaMemcpyDeviceToHost, stream));
+        LGR_CUDA_TRY(cudaMemcpyAsync(host_hdr, geo.offsets + (P - 1), 2 * sizeof(int), cudaMemcpyDeviceToHost, stream));
         LGR_CUDA_TRY(cudaStreamSynchronize(stream));
-        R = host_R[0];       // instances actually emitted (after exact tile culling)
-        R_ref = host_R[1];   // the reference's num_rendered: sum of the tile-rectangle areas
-    }
-    bin = carve_binning(nullptr, (size_t)R, W, H);
-    char* bin_blob = binning_alloc(binning_user, bin.total);
-    if (!bin_blob) { g_last_error = "binning allocator returned NULL"; return LGR_ERR_ALLOC; }
-    bin = carve_binning(bin_blob, (size_t)R, W, H);
+        R = host_hdr[0];       // instances actually emitted (after exact tile culling)
+        R_ref = host_hdr[1];   // the reference's num_rendered: sum of the tile-rectangle areas
+        bin = carve_binning(nullptr, (size_t)R, W, H, true);
+        char* bin_blob = binning_alloc(binning_user, bin.total);
+        if (!bin_blob) { g_last_error = "binning allocator returned NULL"; return LGR_ERR_ALLOC; }
+        bin = carve_binning(bin_blob, (size_t)R, W, H, true);
+        set_capacity_kernel<<<1, 32, 0, stream>>>(geo.num_rendered, R > 0 ? R : 1);
+        LGR_LAUNCH_CHECK("set_capacity_kernel", debug, stream);
 
-    if (R > 0) {
-        const int blocks = (P + 255) / 256;
-        const int bits = tile_key_bits(W, H);
-        size_t tmp = bin.cub_temp_bytes;
-        if (bin.wide_keys) {
-            {
-                ProfScope ps(ST_EMIT, stream);
-                emit_kernel<uint32_t><<<blocks, 256, 0, stream>>>(P, geo.sorted_ids, geo.offsets, geo.tiles_kept, geo.keep_mask, geo.means2D,
-                                                                   radii, gx, gy, (uint32_t*)bin.keys_unsorted, bin.ids_unsorted);
+        if (R > 0) {
+            const int blocks = (P + 255) / 256;
+            const int bits = tile_key_bits(W, H);
+            tmp = bin.cub_temp_bytes;
+            if (bin.wide_keys) {
+                {
+                    ProfScope ps(ST_EMIT, stream);
+                    emit_kernel<uint32_t><<<blocks, 256, 0, stream>>>(P, geo.sorted_ids, geo.offsets, geo.tiles_kept, geo.keep_mask, geo.means2D,
+                                                                       radii, gx, gy, (uint32_t*)bin.keys_unsorted, bin.ids_unsorted);
+                }
+                LGR_LAUNCH_CHECK("emit_kernel", debug, stream);
+                {
+                    ProfScope ps(ST_TILE_SORT, stream);
+                    LGR_CUDA_TRY(cub::DeviceRadixSort::SortPairs(bin.cub_temp, tmp, (const uint32_t*)bin.keys_unsorted,
+                                                                  (uint32_t*)bin.keys_sorted, (const uint32_t*)bin.ids_unsorted,
+                                                                  bin.point_list, R, 0, bits, stream));
+                }
+                ProfScope ps(ST_RANGES, stream);
+                ranges_kernel<uint32_t><<<(gx * gy + 255) / 256, 256, 0, stream>>>(R, gx * gy, (const uint32_t*)bin.keys_sorted, img.ranges);
+            } else {
+                {
+                    ProfScope ps(ST_EMIT, stream);
+                    emit_kernel<uint16_t><<<blocks, 256, 0, stream>>>(P, geo.sorted_ids, geo.offsets, geo.tiles_kept, geo.keep_mask, geo.means2D,
+                                                                       radii, gx, gy, (uint16_t*)bin.keys_unsorted, bin.ids_unsorted);
+                }
+                LGR_LAUNCH_CHECK("emit_kernel", debug, stream);
+                {
+                    ProfScope ps(ST_TILE_SORT, stream);
+                    LGR_CUDA_TRY(cub::DeviceRadixSort::SortPairs(bin.cub_temp, tmp, (const uint16_t*)bin.keys_unsorted,
+                                                                  (uint16_t*)bin.keys_sorted, (const uint32_t*)bin.ids_unsorted,
+                                                                  bin.point_list, R, 0, bits, stream));
+                }
+                ProfScope ps(ST_RANGES, stream);
+                ranges_kernel<uint16_t><<<(gx * gy + 255) / 256, 256, 0, stream>>>(R, gx * gy, (const uint16_t*)bin.keys_sorted, img.ranges);
             }
-            LGR_LAUNCH_CHECK("emit_kernel", debug, stream);
-            {
-                ProfScope ps(ST_TILE_SORT, stream);
-                LGR_CUDA_TRY(cub::DeviceRadixSort::SortPairs(bin.cub_temp, tmp, (const uint32_t*)bin.keys_unsorted,
-                                                              (uint32_t*)bin.keys_sorted, (const uint32_t*)bin.ids_unsorted,
-                                                              bin.point_list, R, 0, bits, stream));
-            }
-            ProfScope ps(ST_RANGES, stream);
-            ranges_kernel<uint32_t><<<(gx * gy + 255) / 256, 256, 0, stream>>>(R, gx * gy, (const uint32_t*)bin.keys_sorted, img.ranges);
-        } else {
-            {
-                ProfScope ps(ST_EMIT, stream);
-                emit_kernel<uint16_t><<<blocks, 256, 0, stream>>>(P, geo.sorted_ids, geo.offsets, geo.tiles_kept, geo.keep_mask, geo.means2D,
-                                                                   radii, gx, gy, (uint16_t*)bin.keys_unsorted, bin.ids_unsorted);
-            }
-            LGR_LAUNCH_CHECK("emit_kernel", debug, stream);
-            {
-                ProfScope ps(ST_TILE_SORT, stream);
-                LGR_CUDA_TRY(cub::DeviceRadixSort::SortPairs(bin.cub_temp, tmp, (const uint16_t*)bin.keys_unsorted,
-                                                              (uint16_t*)bin.keys_sorted, (const uint32_t*)bin.ids_unsorted,
-                                                              bin.point_list, R, 0, bits, stream));
-            }
-            ProfScope ps(ST_RANGES, stream);
-            ranges_kernel<uint16_t><<<(gx * gy + 255) / 256, 256, 0, stream>>>(R, gx * gy, (const uint16_t*)bin.keys_sorted, img.ranges);
+            LGR_LAUNCH_CHECK("ranges_kernel", debug, stream);
         }
-        LGR_LAUNCH_CHECK("ranges_kernel", debug, stream);
-    }
-    if (count_mode && P > 0) LGR_CUDA_TRY(cudaMemsetAsync(gaussians_count, 0, sizeof(int) * (size_t)P, stream));
-    {
-        const int tiles = gx * gy;
-        ProfScope ps(count_mode ? ST_BLEND_FWD_COUNT : ST_BLEND_FWD, stream);
-        if (g_blend_mode == 0 && count_mode)
-            blend_forward_ring_kernel<true, false><<<tiles, BL_THREADS, 0, stream>>>(img.ranges, bin.point_list, W, H, gx, geo.means2D, geo.conic_opacity,
-                                                                                      geo.rgb, v->background, img.final_T, img.n_contrib, out_color,
-                                                                                      gaussians_count, nullptr);
-        else if (g_blend_mode == 0)
-            blend_forward_ring_kernel<false, true><<<tiles, BL_THREADS, 0, stream>>>(img.ranges, bin.point_list, W, H, gx, geo.means2D, geo.conic_opacity,
-                                                                                      geo.rgb, v->background, img.final_T, img.n_contrib, out_color,
-                                                                                      nullptr, bin.records);
-        else if (count_mode)
-            blend_forward_kernel<true><<<tiles, 256, 0, stream>>>(img.ranges, bin.point_list, W, H, gx, geo.means2D, geo.conic_opacity,
-                                                                   geo.rgb, v->background, img.final_T, img.n_contrib, out_color,
-                                                                   gaussians_count);
-        else
-            blend_forward_kernel<false><<<tiles, 256, 0, stream>>>(img.ranges, bin.point_list, W, H, gx, geo.means2D, geo.conic_opacity,
-                                                                    geo.rgb, v->background, img.final_T, img.n_contrib, out_color,
-                                                                    nullptr);
-        LGR_LAUNCH_CHECK("blend_forward_kernel", debug, stream);
+        const int st = launch_blend();
+        if (st != LGR_OK) return st;
     }
     if (count_mode && P > 0) {
         ProfScope ps(ST_SCORE, stream);
@@ -1164,6 +1349,29 @@ int lgr_set_blend_mode(int mode)
     g_blend_mode = mode;
     return LGR_OK;
 }
+
+int lgr_set_binning_mode(int mode)
+{
+    if (mode < 0 || mode > 2) {
+        g_last_error = "lgr_set_binning_mode: 0 = hand-written kernels, estimated blob size (default), 1 = hand-written kernels, exact blob size, 2 = library sorts";
+        return LGR_ERR_INVALID_ARG;
+    }
+    g_bin_mode = mode;
+    return LGR_OK;
+}
+
+int lgr_set_kback_mode(int mode)
+{
+    if (mode != 0 && mode != 1) {
+        g_last_error = "lgr_set_kback_mode: 0 = zero-fill + compacted K7+K8 (default), 1 = dense K7+K8 kernel";
+        return LGR_ERR_INVALID_ARG;
+    }
+    g_kback_mode = mode;
+    return LGR_OK;
+}
+
+uint64_t lgr_binning_overflows(void) { return g_bin_overflows.load(); }
+void lgr_set_binning_estimate(uint64_t instances) { g_bin_hint.store((size_t)instances); }
 
 int lgr_set_tile_culling(int on)
 {
@@ -1207,21 +1415,21 @@ int lgr_profile_collect(double* ms_out, uint64_t* launches_out, int n)
 
 size_t lgr_geometry_layout(int P, size_t* out, int n_out)
 {
-    GeometryState g = carve_geometry(nullptr, (size_t)(P > 0 ? P : 1));
+    GeometryState g = carve_geometry(nullptr, (size_t)(P > 0 ? P : 1), g_bin_mode == 2);
     for (int k = 0; k < n_out && k < 8; k++) out[k] = g.offs[k];
     return g.total;
 }
 
 size_t lgr_image_layout(int width, int height, size_t* out, int n_out)
 {
-    ImageState s = carve_image(nullptr, width, height);
+    ImageState s = carve_image(nullptr, width, height, g_bin_mode == 2);
     for (int k = 0; k < n_out && k < 3; k++) out[k] = s.offs[k];
     return s.total;
 }
 
 size_t lgr_binning_layout(int num_rendered, int width, int height, size_t* out, int n_out)
 {
-    BinningState b = carve_binning(nullptr, (size_t)(num_rendered > 0 ? num_rendered : 0), width, height);
+    BinningState b = carve_binning(nullptr, (size_t)(num_rendered > 0 ? num_rendered : 0), width, height, g_bin_mode == 2);
     for (int k = 0; k < n_out && k < 1; k++) out[k] = b.offs[k];
     return b.total;
 }
@@ -1268,9 +1476,9 @@ int lgr_backward(const lgr_view* v, int P, int M, int num_rendered, const float*
     const bool debug = v->debug != 0;
     const int W = v->image_width, H = v->image_height;
     const int gx = (W + LGR_TILE - 1) / LGR_TILE, gy = (H + LGR_TILE - 1) / LGR_TILE;
-    GeometryState geo = carve_geometry(geometry_blob, (size_t)P);
-    ImageState img = carve_image(image_blob, W, H);
-    BinningState bin = carve_binning(binning_blob, (size_t)(num_rendered > 0 ? num_rendered : 0), W, H);
+    GeometryState geo = carve_geometry(geometry_blob, (size_t)P, false);
+    ImageState img = carve_image(image_blob, W, H, false);
+    BinningState bin = carve_binning(binning_blob, (size_t)(num_rendered > 0 ? num_rendered : 0), W, H, false);
 
     {
         ProfScope ps(ST_MEMSET, stream);
@@ -1336,9 +1544,9 @@ int lgr_backward_raw_begin(const lgr_view* v, int P, int num_rendered, const int
     const bool debug = v->debug != 0;
     const int W = v->image_width, H = v->image_height;
     const int gx = (W + LGR_TILE - 1) / LGR_TILE, gy = (H + LGR_TILE - 1) / LGR_TILE;
-    GeometryState geo = carve_geometry(geometry_blob, (size_t)P);
-    ImageState img = carve_image(image_blob, W, H);
-    BinningState bin = carve_binning(binning_blob, (size_t)(num_rendered > 0 ? num_rendered : 0), W, H);
+    GeometryState geo = carve_geometry(geometry_blob, (size_t)P, false);
+    ImageState img = carve_image(image_blob, W, H, false);
+    BinningState bin = carve_binning(binning_blob, (size_t)(num_rendered > 0 ? num_rendered : 0), W, H, false);
     {
         ProfScope ps(ST_MEMSET, stream);
         LGR_CUDA_TRY(cudaMemsetAsync(geo.grad_acc, 0, sizeof(float) * ACC_STRIDE * (size_t)P, stream));
@@ -1395,7 +1603,7 @@ int lgr_backward_raw_end_range(const lgr_view* v, int P, int M, const lgr_raw_pa
     }
     const bool debug = v->debug != 0;
     const int W = v->image_width, H = v->image_height;
-    GeometryState geo = carve_geometry(geometry_blob, (size_t)P);
+    GeometryState geo = carve_geometry(geometry_blob, (size_t)P, false);
     RawBackArgs a;
     a.P = P; a.D = v->sh_degree; a.M = M; a.W = W; a.H = H;
     a.fy = H / (2.0f * v->tan_fovy);
@@ -1416,6 +1624,25 @@ int lgr_backward_raw_end_range(const lgr_view* v, int P, int M, const lgr_raw_pa
     a.block0 = first / 256;
     a.P = first + count;                       // the kernel's bound check: blocks of this launch never run past the range
     if (compact) { a.d_rest = nullptr; a.d_dc = nullptr; }
+    if (!compact && first == 0 && count == P && g_kback_mode == 0) {
+        // whole view, dense outputs: zero-fill + flag, then K7+K8 on the compacted list of Gaussians with a non-zero gradient
+        // (lgr_sparse.cuh).  The id list reuses sorted_ids (dead after the forward's binning), the count a header word.
+        ProfScope ps(ST_PREPROCESS_BWD, stream);
+        int* counter = geo.num_rendered + HDR_LIVE;
+        LGR_CUDA_TRY(cudaMemsetAsync(counter, 0, sizeof(int), stream));
+        KbackZeroArgs z;
+        z.P = P; z.nrest = (M - 1) * 3; z.radii = radii; z.acc = geo.grad_acc; z.idx = reinterpret_cast<int*>(geo.sorted_ids); z.counter = counter;
+        z.d_xyz = a.d_xyz; z.d_dc = a.d_dc; z.d_rest = a.d_rest; z.d_scaling = a.d_scaling; z.d_rotation = a.d_rotation; z.d_opacity = a.d_opacity;
+        z.dL_dmeans2D = dL_dmeans2D;
+        if (M == 1) z.d_rest = a.d_dc;   // no rest coefficients: nrest = 0, pointer unused
+        kback_zero_flag_kernel<<<(P + 255) / 256, 256, 0, stream>>>(z);
+        LGR_LAUNCH_CHECK("kback_zero_flag_kernel", debug, stream);
+        a.P = P;
+        const int blocks = std::min((P + 255) / 256, 148 * 8);
+        preprocess_backward_compact_kernel<<<blocks, 256, 0, stream>>>(a, reinterpret_cast<const int*>(geo.sorted_ids), counter);
+        LGR_LAUNCH_CHECK("preprocess_backward_compact_kernel", debug, stream);
+        return LGR_OK;
+    }
     const size_t smem = raw_smem_bytes(M);
     LGR_CUDA_TRY(cudaFuncSetAttribute(preprocess_backward_raw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     {
@@ -1483,7 +1710,7 @@ int lgr_backward_raw_sparse_pack_push(const lgr_view* v, int P, int M, const lgr
     }
     const bool debug = v->debug != 0;
     const int W = v->image_width, H = v->image_height;
-    GeometryState geo = carve_geometry(geometry_blob, (size_t)P);
+    GeometryState geo = carve_geometry(geometry_blob, (size_t)P, false);
     const SparseLayout L = sparse_layout(P);
     uint32_t* xb = push.dst[self];
     const int w32 = (P + 31) / 32;

@@ -162,3 +162,18 @@ def test_strided_student_features_rest_takes_the_fused_path(P):
     c1 = renderer.count_render(cam, stu, pipe, bg)
     c2 = renderer.count_render(cam, con, pipe, bg)
     assert torch.equal(c1["gaussians_count"], c2["gaussians_count"]) and torch.equal(c1["render"], c2["render"])
+
+
+def test_dense_kback_kernel_still_agrees():
+    """lgr_set_kback_mode(1): the one-warp-per-32-Gaussians K7+K8 kernel (used for ranged / compact launches of the exchange paths)
+    against the plain path, like the default zero-fill + compacted-list pair above"""
+    from lightgaussian_b200 import capi
+    capi.set_kback_mode(1)
+    try:
+        o = _render_both(3000 + 5, 128, 96, 3, 16, make_cameras(5, 128, 96)[2], seed=21)
+    finally:
+        capi.set_kback_mode(0)
+    f, p = o["fused"], o["plain"]
+    np.testing.assert_array_equal(f["render"], p["render"])
+    for a, b in zip(f["grads"], p["grads"]):
+        assert rel_inf(a, b) <= 1e-3 and rel_l2(a, b) <= 1e-4

@@ -52,7 +52,7 @@ def _empty():
 
 
 def run_ours(view: View, act: dict, count=False, dL_dpix=None, colors_precomp=None, cov3D_precomp=None, debug=False, tile_cull=True,
-             blend_mode=0):
+             blend_mode=0, bin_mode=0):
     """tile_cull=False makes the per-tile lists identical to the reference's (needed to compare point_list / ranges /
     n_contrib); the product default (True) lists only instances that can contribute."""
     import torch
@@ -61,11 +61,13 @@ def run_ours(view: View, act: dict, count=False, dL_dpix=None, colors_precomp=No
     dev = "cuda"
     capi.set_tile_culling(tile_cull)
     capi.set_blend_mode(blend_mode)      # 0 = ring kernels (the product default), 1 = the round-1 kernels
+    capi.set_binning_mode(bin_mode)      # 0 = hand-written binning, estimated blob (default); 1 = exact blob; 2 = round-1 library sorts
     try:
         return _run_ours(view, act, count, dL_dpix, colors_precomp, cov3D_precomp, debug)
     finally:
         capi.set_tile_culling(True)
         capi.set_blend_mode(0)
+        capi.set_binning_mode(0)
 
 
 def _run_ours(view, act, count, dL_dpix, colors_precomp, cov3D_precomp, debug):
@@ -252,13 +254,26 @@ def elem_rel(a, b, floor=1e-6):
     return e, int(m.sum())
 
 
-def assert_elementwise(a, b, name, tol=1e-3, frac=0.995, median=2e-5):
-    """at least `frac` of the entries with |b| > 1e-6 agree to `tol` relative, and the median relative error is <= `median`"""
+def assert_elementwise(a, b, name, tol=1e-3, frac=0.995, median=2e-5, exact=None):
+    """at least `frac` of the entries with |b| > 1e-6 agree to `tol` relative, and the median relative error is <= `median`.
+
+    `exact` (optional) = the same gradient from the float64 oracle.  The reference's float atomics (backward.cu:523-541) make ITS
+    small entries wander at the 1e-3 level from run to run on scenes with screen-filling splats, so there the arbiter is the exact
+    value: our `frac` quantile of |a - exact| / |exact| must stay below `tol` or below 1.5x the reference's own quantile, and the
+    direct comparison is bounded at 3 * tol."""
     e, n = elem_rel(a, b)
     if n == 0:
         return
     q = e[min(n - 1, int(frac * n))]
-    assert q <= tol, f"{name}: {100 * frac:.1f} % quantile of the per-element relative error is {q:.2e} (> {tol:g}; n = {n})"
+    if exact is not None:
+        ea, na = elem_rel(a, exact)
+        eb, nb = elem_rel(b, exact)
+        qa, qb = ea[min(na - 1, int(frac * na))], eb[min(nb - 1, int(frac * nb))]
+        assert qa <= max(tol, 1.5 * qb), (f"{name}: {100 * frac:.1f} % quantile of our per-element error against the float64 oracle is {qa:.2e} "
+                                          f"(reference kernels: {qb:.2e}; n = {na})")
+        assert q <= 3 * tol, f"{name}: {100 * frac:.1f} % quantile of the per-element relative error vs the reference is {q:.2e} (n = {n})"
+    else:
+        assert q <= tol, f"{name}: {100 * frac:.1f} % quantile of the per-element relative error is {q:.2e} (> {tol:g}; n = {n})"
     assert e[n // 2] <= median, f"{name}: median per-element relative error {e[n // 2]:.2e} (> {median:g})"
 
 
