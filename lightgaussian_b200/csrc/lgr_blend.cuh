@@ -80,6 +80,59 @@ __device__ __forceinline__ bool subtile_cull2(float gxp, float gyp, float A, flo
     return qmin > thr + 2.0e-6f * mag;
 }
 
+// ---- zero-fill of the dense per-Gaussian gradient rows (see lgr_sparse.cuh, "Single-GPU K7+K8 on the compacted list") ----
+constexpr int KB_ZERO_BYTES = 5760;   // 32 rows x 45 floats: the dense dL/dfeatures_rest run of one warp at degree 3
+
+struct KbackZeroArgs {
+    int P, nrest;
+    const int* radii;
+    const float* acc;
+    int* idx;        // [P] out: ids with a non-zero gradient (unordered)
+    int* counter;    // out: how many
+    float* d_xyz; float* d_dc; float* d_rest; float* d_scaling; float* d_rotation; float* d_opacity; float* dL_dmeans2D;
+};
+
+__device__ __forceinline__ void bulk_zero(float* dst, size_t floats, const void* zero_page)
+{
+    size_t bytes = floats * 4;
+    char* p = reinterpret_cast<char*>(dst);
+    while (bytes) {
+        const uint32_t n = (uint32_t)(bytes < (size_t)KB_ZERO_BYTES ? bytes : (size_t)KB_ZERO_BYTES);
+        bulk_s2g(p, zero_page, n);
+        p += n;
+        bytes -= n;
+    }
+}
+
+
+// the tile's share of the rows: tiles split [0, P) into runs of G Gaussians, G a multiple of 4 so that every run of every tensor starts
+// 16-byte aligned and is a multiple of 16 bytes (cp.async.bulk's granularity); the tail that is not is cleared with plain stores
+__device__ __forceinline__ void tile_zero_rows(const KbackZeroArgs& z, int tile, int tiles, const void* zero_page)
+{
+    const int G = ((z.P + tiles - 1) / tiles + 3) & ~3;
+    const long long first = (long long)tile * G;
+    if (first >= z.P) return;
+    const int n = (int)min((long long)G, z.P - first), nb = n & ~3;
+    if (nb) {
+        bulk_zero(z.d_rest + (size_t)first * z.nrest, (size_t)nb * z.nrest, zero_page);
+        bulk_zero(z.d_dc + (size_t)first * 3, (size_t)nb * 3, zero_page);
+        bulk_zero(z.d_xyz + (size_t)first * 3, (size_t)nb * 3, zero_page);
+        bulk_zero(z.d_scaling + (size_t)first * 3, (size_t)nb * 3, zero_page);
+        bulk_zero(z.d_rotation + (size_t)first * 4, (size_t)nb * 4, zero_page);
+        bulk_zero(z.d_opacity + (size_t)first, (size_t)nb, zero_page);
+        bulk_zero(z.dL_dmeans2D + (size_t)first * 3, (size_t)nb * 3, zero_page);
+        bulk_commit();
+    }
+    for (long long i = first + nb; i < first + n; i++) {   // at most 3 Gaussians, last run only
+        for (int k = 0; k < z.nrest; k++) z.d_rest[(size_t)i * z.nrest + k] = 0.f;
+        for (int k = 0; k < 3; k++) {
+            z.d_dc[(size_t)i * 3 + k] = 0.f; z.d_xyz[(size_t)i * 3 + k] = 0.f; z.d_scaling[(size_t)i * 3 + k] = 0.f; z.dL_dmeans2D[(size_t)i * 3 + k] = 0.f;
+        }
+        for (int k = 0; k < 4; k++) z.d_rotation[(size_t)i * 4 + k] = 0.f;
+        z.d_opacity[(size_t)i] = 0.f;
+    }
+}
+
 struct BlendRing {
     float rec[BL_STAGES][BL_CH * BL_REC];
     uint64_t full[BL_STAGES];
@@ -313,12 +366,15 @@ __device__ __forceinline__ void back_flush(const BlendBackWarp& bw, int nbuf, in
     __syncwarp();
 }
 
-constexpr size_t blend_back_smem_bytes() { return sizeof(BlendRing) + 128 + 8 * sizeof(BlendBackWarp); }
+constexpr size_t blend_back_smem_bytes(bool zero_rows = false)
+{
+    return (sizeof(BlendRing) + 127) / 128 * 128 + (8 * sizeof(BlendBackWarp) + 127) / 128 * 128 + (zero_rows ? (size_t)KB_ZERO_BYTES : 0);
+}
 
 __global__ void __launch_bounds__(BL_THREADS)
 blend_backward_ring_kernel(const uint2* __restrict__ ranges, const char* __restrict__ binning_blob, const int* __restrict__ header, int W, int H,
                            int tiles_x, const float* __restrict__ bg, const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib,
-                           const float* __restrict__ dL_dpix, float* __restrict__ acc)
+                           const float* __restrict__ dL_dpix, float* __restrict__ acc, KbackZeroArgs zero)
 {
     extern __shared__ __align__(128) unsigned char blend_dyn_smem[];
     BlendRing& ring = *reinterpret_cast<BlendRing*>(blend_dyn_smem);
@@ -326,7 +382,16 @@ blend_backward_ring_kernel(const uint2* __restrict__ ranges, const char* __restr
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile = blockIdx.x;
     const uint2 range = ranges[tile];
+    // zero.P > 0: this launch also clears the dense gradient rows K7+K8 will (sparsely) write -- a page of zeros behind the per-warp
+    // buffers, one thread, a handful of bulk stores per tile; the HBM writes overlap the blend, which leaves DRAM ~97 % idle
+    float* zero_page = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(warps) + (8 * sizeof(BlendBackWarp) + 127) / 128 * 128);
+    const bool zero_rows = zero.P > 0;
+    if (zero_rows) {
+        for (int k = threadIdx.x; k < KB_ZERO_BYTES / 4; k += BL_THREADS) zero_page[k] = 0.f;
+        fence_async_smem();
+    }
     ring_init(ring, 8);
+    if (zero_rows && threadIdx.x == 8 * 32) tile_zero_rows(zero, tile, gridDim.x, zero_page);
 
     const int tx = tile % tiles_x, ty = tile / tiles_x;
     const int sx0 = tx * LGR_TILE + (warp & 1) * 8, sy0 = ty * LGR_TILE + (warp >> 1) * 4;
@@ -339,7 +404,10 @@ blend_backward_ring_kernel(const uint2* __restrict__ ranges, const char* __restr
     if (lane == 0 && warp_max) atomicMax(&ring.tile_max, warp_max);
     __syncthreads();
     const uint32_t tile_max = ring.tile_max;
-    if (tile_max == 0) return;
+    if (tile_max == 0) {
+        if (zero_rows && threadIdx.x == 8 * 32) bulk_wait_all();   // the zero page must outlive the stores that read it
+        return;
+    }
     const uint32_t nchunks = (tile_max + BL_CH - 1) / BL_CH;
 
     if (warp == 8) {
@@ -359,6 +427,7 @@ blend_backward_ring_kernel(const uint2* __restrict__ ranges, const char* __restr
                 mbar_expect_tx(&ring.full[s], bytes);
                 bulk_g2s(&ring.rec[s][0], rec_in + ((size_t)range.x + (size_t)b * BL_CH) * BL_REC, bytes, &ring.full[s]);
             }
+            if (zero_rows) bulk_wait_all();   // long done by now
         }
         return;
     }

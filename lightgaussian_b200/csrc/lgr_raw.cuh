@@ -163,6 +163,8 @@ __global__ void __launch_bounds__(256) preprocess_raw_kernel(RawArgs a, int* __r
     if (any_vis) bulk = warp_stage_sh_begin(a.rest, a.dc, nrest, first, n, s_rest, s_dc, &bars[warp], lane);
 
     // everything that does not need the SH rows overlaps the copy
+    const float op_act = visible ? act_sigmoid(a.opacity[i]) : 0.f;
+    const unsigned long long keep_bits = warp_tile_keep_mask(visible, geo, make_float4(geo.conic_x, geo.conic_y, geo.conic_z, op_act), a.W, a.H, lane);
     if (valid) {
         if (!g.bin_rec) g.iota[i] = (uint32_t)i;
         if (!visible) {
@@ -177,13 +179,12 @@ __global__ void __launch_bounds__(256) preprocess_raw_kernel(RawArgs a, int* __r
             g.depth[i] = geo.depth;
             g.depth_keys[i] = __float_as_uint(geo.depth);
             g.means2D[i] = make_float2(geo.px, geo.py);
-            const float4 co = make_float4(geo.conic_x, geo.conic_y, geo.conic_z, act_sigmoid(a.opacity[i]));
+            const float4 co = make_float4(geo.conic_x, geo.conic_y, geo.conic_z, op_act);
             g.conic_opacity[i] = co;
             const uint32_t area = (uint32_t)((geo.rect.y1 - geo.rect.y0) * (geo.rect.x1 - geo.rect.x0));
             g.tiles_touched[i] = area;
-            unsigned long long mask;
-            uint32_t kept;
-            tile_keep_mask(geo, co, a.W, a.H, mask, kept);
+            const unsigned long long mask = keep_bits;
+            const uint32_t kept = area > 64u ? area : (uint32_t)__popcll(mask);
             if (g.bin_rec) {
                 g.bin_rec[i] = make_bin_rec(geo.rect.x0, geo.rect.y0, geo.rect.x1 - geo.rect.x0, geo.rect.y1 - geo.rect.y0, mask);
             } else {

@@ -248,45 +248,27 @@ __global__ void __launch_bounds__(256) sparse_accumulate_kernel(SparseAccArgs a)
 // Single-GPU K7+K8 on the compacted list (the dense kernel spends a full warp pass on every 32 Gaussians that hold even ONE
 // non-zero gradient -- 99 % of the warps at 13 % density -- and re-reads 0.7 GB of parameters for rows that come out as zeros).
 //
-//   kback_zero_flag_kernel    one pass over the 48-byte accumulator records: flags the Gaussians with a non-zero gradient, appends
-//                             their ids to a list (one atomicAdd per warp), and zero-fills EVERY dense output row of the block's 256
-//                             Gaussians with TMA bulk stores from one shared page of zeros (14 cp.async.bulk per block, issued by
-//                             one thread; no per-lane store instructions).
+//   zero-fill                 EVERY dense output row is cleared with TMA bulk stores from one shared page of zeros (cp.async.bulk S2G,
+//                             issued by one thread; no per-lane store instructions) -- by default from inside the blend backward
+//                             (lgr_blend.cuh: its producer thread clears the tile's share of the rows while the kernel, which is
+//                             instruction-issue-bound and leaves HBM idle, does its work), else by kback_zero_flag_kernel<true>.
+//   kback_zero_flag_kernel    one pass over the 48-byte accumulator records: flags the Gaussians with a non-zero gradient and
+//                             appends their ids to a list (one atomicAdd per warp).
 //   preprocess_backward_compact_kernel   K7+K8 with the activation chain rules for the listed Gaussians only (all 32 lanes busy),
 //                             rows written over the zeros.  Grid-stride over the device-side count: no host synchronisation.
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int KB_ZERO_BYTES = 5760;   // 32 rows x 45 floats: the dense dL/dfeatures_rest run of one warp at degree 3
-
-struct KbackZeroArgs {
-    int P, nrest;
-    const int* radii;
-    const float* acc;
-    int* idx;        // [P] out: ids with a non-zero gradient (unordered)
-    int* counter;    // out: how many
-    float* d_xyz; float* d_dc; float* d_rest; float* d_scaling; float* d_rotation; float* d_opacity; float* dL_dmeans2D;
-};
-
-__device__ __forceinline__ void bulk_zero(float* dst, size_t floats, const void* zero_page)
-{
-    size_t bytes = floats * 4;
-    char* p = reinterpret_cast<char*>(dst);
-    while (bytes) {
-        const uint32_t n = (uint32_t)(bytes < (size_t)KB_ZERO_BYTES ? bytes : (size_t)KB_ZERO_BYTES);
-        bulk_s2g(p, zero_page, n);
-        p += n;
-        bytes -= n;
-    }
-}
-
+template <bool ZERO>
 __global__ void __launch_bounds__(256) kback_zero_flag_kernel(KbackZeroArgs a)
 {
-    __shared__ __align__(128) float zero_page[KB_ZERO_BYTES / 4];
-    for (int k = threadIdx.x; k < KB_ZERO_BYTES / 4; k += 256) zero_page[k] = 0.f;
-    fence_async_smem();
-    __syncthreads();
+    __shared__ __align__(128) float zero_page[ZERO ? KB_ZERO_BYTES / 4 : 4];
+    if (ZERO) {
+        for (int k = threadIdx.x; k < KB_ZERO_BYTES / 4; k += 256) zero_page[k] = 0.f;
+        fence_async_smem();
+        __syncthreads();
+    }
     const int first = blockIdx.x * 256;
     const int n = min(256, a.P - first);
-    if (threadIdx.x == 0) {
+    if (ZERO && threadIdx.x == 0) {
         if (n == 256) {   // every run starts 16-byte aligned and is a multiple of 16 bytes
             bulk_zero(a.d_rest + (size_t)first * a.nrest, (size_t)256 * a.nrest, zero_page);
             bulk_zero(a.d_dc + (size_t)first * 3, 768, zero_page);
@@ -298,7 +280,7 @@ __global__ void __launch_bounds__(256) kback_zero_flag_kernel(KbackZeroArgs a)
             bulk_commit();
         }
     }
-    if (n < 256) {   // ragged last block: plain stores
+    if (ZERO && n < 256) {   // ragged last block: plain stores
         for (int k = threadIdx.x; k < n * a.nrest; k += 256) a.d_rest[(size_t)first * a.nrest + k] = 0.f;
         for (int k = threadIdx.x; k < n * 3; k += 256) {
             a.d_dc[(size_t)first * 3 + k] = 0.f; a.d_xyz[(size_t)first * 3 + k] = 0.f; a.d_scaling[(size_t)first * 3 + k] = 0.f;
@@ -321,7 +303,7 @@ __global__ void __launch_bounds__(256) kback_zero_flag_kernel(KbackZeroArgs a)
     if (lane == 0 && word) base = atomicAdd(a.counter, __popc(word));
     base = __shfl_sync(FULL, base, 0);
     if (nz) a.idx[base + __popc(word & ((1u << lane) - 1u))] = i;
-    if (threadIdx.x == 0 && n == 256) bulk_wait_read_all();   // the zero page must outlive the copies that read it
+    if (ZERO && threadIdx.x == 0 && n == 256) bulk_wait_read_all();   // the zero page must outlive the copies that read it
 }
 
 __global__ void __launch_bounds__(256) preprocess_backward_compact_kernel(RawBackArgs a, const int* __restrict__ idx, const int* __restrict__ counter)

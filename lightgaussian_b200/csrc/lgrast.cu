@@ -47,7 +47,7 @@ int g_blend_mode = 0;   // 0 = ring kernels (lgr_blend.cuh), 1 = round-1 kernels
 // binning (lgr_bin.cuh): 0 = hand-written kernels, binning blob sized from a running estimate, no GPU idle on the host (default);
 // 1 = hand-written kernels, blob sized exactly after a stream synchronisation; 2 = round-1 path (library radix sorts + scan, host sync)
 int g_bin_mode = 0;
-int g_kback_mode = 0;   // single-GPU fused K7+K8: 0 = zero-fill + compacted list (lgr_sparse.cuh), 1 = dense kernel (A/B)
+int g_kback_mode = 0;   // single-GPU K7+K8: 0 = rows cleared inside the blend backward + compacted list (lgr_sparse.cuh), 1 = dense kernel, 2 = separate zero-fill kernel + compacted list (A/B)
 std::atomic<size_t> g_bin_hint{0};   // running estimate of the listed instances per view (mode 0)
 std::atomic<uint64_t> g_launches{0};
 
@@ -380,6 +380,86 @@ __device__ __forceinline__ void tile_keep_mask(const lgr::Geom& geo, float4 co, 
     }
     mask = m;
     kept = (uint32_t)__popcll(m);
+}
+
+// The same mask for the 32 Gaussians of a warp, evaluated warp-cooperatively: the (Gaussian, tile) candidates of the warp are laid
+// out back to back, lane L tests candidates L, L+32, ... (owner found with a 5-step shuffle search, its hoisted coefficients fetched by
+// shuffle), one ballot per step returns the keep bits and every owner cuts its own bits out of it.  ~6 steps per warp instead of a
+// per-lane loop as long as the largest rectangle in the warp (thread efficiency 17/32 in the per-lane version, profiles/r01c).
+// All 32 lanes must call it; `visible` lanes get their mask, the others 0.  Same arithmetic as tile_keep_mask() => same masks.
+__device__ __forceinline__ unsigned long long warp_tile_keep_mask(bool visible, const lgr::Geom& geo, float4 co, int W, int H, int lane)
+{
+    const int w = visible ? geo.rect.x1 - geo.rect.x0 : 0, h = visible ? geo.rect.y1 - geo.rect.y0 : 0;
+    const int area = w * h;
+    unsigned long long mask = area >= 64 ? ~0ull : ((1ull << area) - 1ull);
+    const float A = co.x, B = co.y, Cc = co.z;
+    const float t = 257.55f * co.w;
+    uint32_t need = 0;
+    if (visible && area <= 64 && g_tile_cull_enabled) {
+        if (t <= 1.0f) mask = 0ull;
+        else if (A > 0.f && Cc > 0.f && A * Cc - B * B > 0.f) need = (uint32_t)area;
+    }
+    uint32_t incl = need;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t v = __shfl_up_sync(FULL, incl, d);
+        if (lane >= d) incl += v;
+    }
+    const uint32_t off = incl - need, total = __shfl_sync(FULL, incl, 31);
+    if (total == 0) return mask;
+    const float thr = __logf(fmaxf(t, 1.0f));
+    const float nbc = __fdividef(-B, Cc), nba = __fdividef(-B, A), hA = 0.5f * A, hC = 0.5f * Cc;
+    const int packed = visible ? (geo.rect.x0 | (geo.rect.y0 << 12) | (w << 24)) : (1 << 24);   // w <= 64 here; x0, y0 < 4096 tiles
+    const float px = visible ? geo.px : 0.f, py = visible ? geo.py : 0.f;
+    unsigned long long kept = 0ull;
+    for (uint32_t base = 0; base < total; base += 32) {
+        const uint32_t j = base + lane;
+        int lo = 0, hi = 31;   // largest lane m with off[m] <= j
+#pragma unroll
+        for (int it = 0; it < 5; it++) {
+            const int mid = (lo + hi + 1) >> 1;
+            const uint32_t v = __shfl_sync(FULL, off, mid);
+            if (v <= j) lo = mid;
+            else hi = mid - 1;
+        }
+        const uint32_t o_off = __shfl_sync(FULL, off, lo);
+        const int o_pk = __shfl_sync(FULL, packed, lo);
+        const float o_px = __shfl_sync(FULL, px, lo), o_py = __shfl_sync(FULL, py, lo);
+        const float o_hA = __shfl_sync(FULL, hA, lo), o_hC = __shfl_sync(FULL, hC, lo), o_B = __shfl_sync(FULL, B, lo);
+        const float o_nbc = __shfl_sync(FULL, nbc, lo), o_nba = __shfl_sync(FULL, nba, lo), o_thr = __shfl_sync(FULL, thr, lo);
+        bool keep = false;
+        if (j < total) {
+            const int o_w = (o_pk >> 24) & 0xff, local = (int)(j - o_off);
+            const int ry = (int)__fdividef((float)local + 0.5f, (float)o_w), rx = local - ry * o_w;
+            const int tx = (o_pk & 0xfff) + rx, ty = ((o_pk >> 12) & 0xfff) + ry;
+            const float dy_lo = o_py - (float)min(ty * LGR_TILE + LGR_TILE - 1, H - 1), dy_hi = o_py - (float)(ty * LGR_TILE);
+            const float cy = fminf(fmaxf(0.f, dy_lo), dy_hi);
+            const float dx_lo = o_px - (float)min(tx * LGR_TILE + LGR_TILE - 1, W - 1), dx_hi = o_px - (float)(tx * LGR_TILE);
+            const float cx = fminf(fmaxf(0.f, dx_lo), dx_hi);
+            float q = 0.f;
+            if (cx != 0.f || cy != 0.f) {
+                q = 3.0e38f;
+                if (cx != 0.f) {
+                    const float dy = fminf(fmaxf(o_nbc * cx, dy_lo), dy_hi);
+                    q = o_hA * cx * cx + o_hC * dy * dy + o_B * cx * dy;
+                }
+                if (cy != 0.f) {
+                    const float dx = fminf(fmaxf(o_nba * cy, dx_lo), dx_hi);
+                    q = fminf(q, o_hA * dx * dx + o_hC * cy * cy + o_B * dx * cy);
+                }
+            }
+            keep = !(q > o_thr);
+        }
+        const unsigned bal = __ballot_sync(FULL, keep);
+        // my candidates inside [base, base + 32)
+        const uint32_t s0 = max(off, base), s1 = min(off + need, base + 32u);
+        if (s0 < s1) {
+            const uint32_t len = s1 - s0;
+            const uint32_t seg = (bal >> (s0 - base)) & (len == 32u ? 0xffffffffu : ((1u << len) - 1u));
+            kept |= (unsigned long long)seg << (s0 - off);
+        }
+    }
+    return need ? kept : mask;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1362,8 +1442,8 @@ int lgr_set_binning_mode(int mode)
 
 int lgr_set_kback_mode(int mode)
 {
-    if (mode != 0 && mode != 1) {
-        g_last_error = "lgr_set_kback_mode: 0 = zero-fill + compacted K7+K8 (default), 1 = dense K7+K8 kernel";
+    if (mode < 0 || mode > 2) {
+        g_last_error = "lgr_set_kback_mode: 0 = rows cleared inside the blend backward + compacted K7+K8 (default), 1 = dense K7+K8 kernel, 2 = separate zero-fill kernel + compacted K7+K8";
         return LGR_ERR_INVALID_ARG;
     }
     g_kback_mode = mode;
@@ -1492,7 +1572,7 @@ int lgr_backward(const lgr_view* v, int P, int M, int num_rendered, const float*
             // start inside the binning blob) sits in the geometry header on the device
             blend_backward_ring_kernel<<<gx * gy, BL_THREADS, blend_back_smem_bytes(), stream>>>(img.ranges, binning_blob, geo.num_rendered, W, H, gx,
                                                                                                    v->background, img.final_T, img.n_contrib,
-                                                                                                   dL_dout_color, geo.grad_acc);
+                                                                                                   dL_dout_color, geo.grad_acc, KbackZeroArgs{});
         } else
             blend_backward_kernel<<<gx * gy, 256, 0, stream>>>(img.ranges, bin.point_list, W, H, gx, geo.means2D, geo.conic_opacity, geo.rgb,
                                                                 v->background, img.final_T, img.n_contrib, dL_dout_color, geo.grad_acc);
@@ -1531,6 +1611,10 @@ int lgr_forward_raw(const lgr_view* view, int P, int M, const lgr_raw_params* pa
                         num_rendered, cuda_stream, count_mode, params);
 }
 
+// lgr_backward_raw (one call for both stages, dense outputs) asks stage 1 to clear the gradient rows from inside the blend backward
+thread_local KbackZeroArgs t_zero_req = {};
+thread_local bool t_rows_zeroed = false;
+
 // stage 1 of the raw backward: clear the accumulators, blend backward, optionally extract this view's dL/dRGB
 int lgr_backward_raw_begin(const lgr_view* v, int P, int num_rendered, const int32_t* radii, char* geometry_blob, char* binning_blob,
                            char* image_blob, const float* dL_dout_color, float* d_rgb, void* cuda_stream)
@@ -1557,9 +1641,14 @@ int lgr_backward_raw_begin(const lgr_view* v, int P, int num_rendered, const int
             LGR_CUDA_TRY(cudaFuncSetAttribute(blend_backward_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blend_back_smem_bytes()));
             // the host only knows the reference's num_rendered here; the number of LISTED instances (which fixes where the records
             // start inside the binning blob) sits in the geometry header on the device
-            blend_backward_ring_kernel<<<gx * gy, BL_THREADS, blend_back_smem_bytes(), stream>>>(img.ranges, binning_blob, geo.num_rendered, W, H, gx,
-                                                                                                   v->background, img.final_T, img.n_contrib,
-                                                                                                   dL_dout_color, geo.grad_acc);
+            const KbackZeroArgs zr = t_zero_req;
+            t_zero_req.P = 0;
+            const size_t bsmem = blend_back_smem_bytes(zr.P > 0);
+            LGR_CUDA_TRY(cudaFuncSetAttribute(blend_backward_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blend_back_smem_bytes(true)));
+            blend_backward_ring_kernel<<<gx * gy, BL_THREADS, bsmem, stream>>>(img.ranges, binning_blob, geo.num_rendered, W, H, gx,
+                                                                                 v->background, img.final_T, img.n_contrib,
+                                                                                 dL_dout_color, geo.grad_acc, zr);
+            t_rows_zeroed = zr.P > 0;
         } else
             blend_backward_kernel<<<gx * gy, 256, 0, stream>>>(img.ranges, bin.point_list, W, H, gx, geo.means2D, geo.conic_opacity, geo.rgb,
                                                                 v->background, img.final_T, img.n_contrib, dL_dout_color, geo.grad_acc);
@@ -1624,9 +1713,12 @@ int lgr_backward_raw_end_range(const lgr_view* v, int P, int M, const lgr_raw_pa
     a.block0 = first / 256;
     a.P = first + count;                       // the kernel's bound check: blocks of this launch never run past the range
     if (compact) { a.d_rest = nullptr; a.d_dc = nullptr; }
-    if (!compact && first == 0 && count == P && g_kback_mode == 0) {
-        // whole view, dense outputs: zero-fill + flag, then K7+K8 on the compacted list of Gaussians with a non-zero gradient
-        // (lgr_sparse.cuh).  The id list reuses sorted_ids (dead after the forward's binning), the count a header word.
+    const bool rows_zeroed = t_rows_zeroed;
+    t_rows_zeroed = false;
+    if (!compact && first == 0 && count == P && g_kback_mode != 1) {
+        // whole view, dense outputs: zero-fill (unless the blend backward already did it) + flag, then K7+K8 on the compacted list of
+        // Gaussians with a non-zero gradient (lgr_sparse.cuh).  The id list reuses sorted_ids (dead after the forward's binning), the
+        // count a header word.
         ProfScope ps(ST_PREPROCESS_BWD, stream);
         int* counter = geo.num_rendered + HDR_LIVE;
         LGR_CUDA_TRY(cudaMemsetAsync(counter, 0, sizeof(int), stream));
@@ -1635,7 +1727,8 @@ int lgr_backward_raw_end_range(const lgr_view* v, int P, int M, const lgr_raw_pa
         z.d_xyz = a.d_xyz; z.d_dc = a.d_dc; z.d_rest = a.d_rest; z.d_scaling = a.d_scaling; z.d_rotation = a.d_rotation; z.d_opacity = a.d_opacity;
         z.dL_dmeans2D = dL_dmeans2D;
         if (M == 1) z.d_rest = a.d_dc;   // no rest coefficients: nrest = 0, pointer unused
-        kback_zero_flag_kernel<<<(P + 255) / 256, 256, 0, stream>>>(z);
+        if (rows_zeroed) kback_zero_flag_kernel<false><<<(P + 255) / 256, 256, 0, stream>>>(z);
+        else kback_zero_flag_kernel<true><<<(P + 255) / 256, 256, 0, stream>>>(z);
         LGR_LAUNCH_CHECK("kback_zero_flag_kernel", debug, stream);
         a.P = P;
         const int blocks = std::min((P + 255) / 256, 148 * 8);
@@ -1657,8 +1750,21 @@ int lgr_backward_raw(const lgr_view* v, int P, int M, int num_rendered, const lg
                      char* geometry_blob, char* binning_blob, char* image_blob, const float* dL_dout_color, const lgr_raw_grads* grads,
                      float* dL_dmeans2D, void* cuda_stream)
 {
+    t_zero_req.P = 0;
+    t_rows_zeroed = false;
+    if (g_kback_mode == 0 && g_blend_mode == 0 && P > 0 && M >= 1 && grads && grads->features_rest != nullptr && grads->features_dc && grads->xyz &&
+        grads->scaling && grads->rotation && grads->opacity && dL_dmeans2D &&
+        !(((uintptr_t)grads->xyz | (uintptr_t)grads->features_dc | (uintptr_t)grads->features_rest | (uintptr_t)grads->scaling |
+           (uintptr_t)grads->rotation | (uintptr_t)grads->opacity | (uintptr_t)dL_dmeans2D) & 15)) {
+        // dense outputs: the blend backward's producer thread clears the rows (runs of 4 Gaussians are 16-byte multiples in every tensor)
+        KbackZeroArgs& z = t_zero_req;
+        z.P = P; z.nrest = (M - 1) * 3; z.radii = nullptr; z.acc = nullptr; z.idx = nullptr; z.counter = nullptr;
+        z.d_xyz = grads->xyz; z.d_dc = grads->features_dc; z.d_rest = grads->features_rest; z.d_scaling = grads->scaling;
+        z.d_rotation = grads->rotation; z.d_opacity = grads->opacity; z.dL_dmeans2D = dL_dmeans2D;
+    }
     const int st = lgr_backward_raw_begin(v, P, num_rendered, radii, geometry_blob, binning_blob, image_blob, dL_dout_color, nullptr, cuda_stream);
-    if (st != LGR_OK) return st;
+    t_zero_req.P = 0;
+    if (st != LGR_OK) { t_rows_zeroed = false; return st; }
     return lgr_backward_raw_end(v, P, M, params, radii, geometry_blob, grads, dL_dmeans2D, cuda_stream);
 }
 

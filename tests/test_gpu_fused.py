@@ -164,11 +164,12 @@ def test_strided_student_features_rest_takes_the_fused_path(P):
     assert torch.equal(c1["gaussians_count"], c2["gaussians_count"]) and torch.equal(c1["render"], c2["render"])
 
 
-def test_dense_kback_kernel_still_agrees():
-    """lgr_set_kback_mode(1): the one-warp-per-32-Gaussians K7+K8 kernel (used for ranged / compact launches of the exchange paths)
-    against the plain path, like the default zero-fill + compacted-list pair above"""
+@pytest.mark.parametrize("mode", [1, 2])
+def test_other_kback_modes_still_agree(mode):
+    """lgr_set_kback_mode(1): the one-warp-per-32-Gaussians K7+K8 kernel (used for ranged / compact launches of the exchange paths);
+    (2): zero-fill in its own kernel instead of inside the blend backward -- against the plain path, like the default above"""
     from lightgaussian_b200 import capi
-    capi.set_kback_mode(1)
+    capi.set_kback_mode(mode)
     try:
         o = _render_both(3000 + 5, 128, 96, 3, 16, make_cameras(5, 128, 96)[2], seed=21)
     finally:

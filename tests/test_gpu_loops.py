@@ -129,3 +129,48 @@ def test_distillation_step_student_sh2_from_teacher_sh3():
         opt.zero_grad(set_to_none=True)
         losses.append(float(loss.detach()))
     assert losses[0] > 0 and np.mean(losses[-5:]) < 0.9 * np.mean(losses[:5]), losses
+
+
+def _finetune_views_per_step(raw, cams, targets, views_per_step, views_total, lr_scale):
+    """prune_finetune.py's loop with `views_per_step` views feeding ONE optimizer step (what N ranks do: each renders one view, the
+    per-Gaussian gradients are SUMMED by the exchange, every rank takes the same AdamW step) -- emulated on one GPU by accumulating
+    the views' gradients.  views_per_step = 1 is the reference's own semantics (prune_finetune.py:144-166, 287-289)."""
+    pc = GaussianParams(raw, 3, "cuda")
+    s = lr_scale
+    opt = torch.optim.Adam([{"params": [pc._xyz], "lr": 1e-4 * s}, {"params": [pc._features_dc], "lr": 1e-2 * s},
+                            {"params": [pc._features_rest], "lr": 5e-4 * s}, {"params": [pc._opacity], "lr": 5e-2 * s},
+                            {"params": [pc._scaling], "lr": 5e-3 * s}, {"params": [pc._rotation], "lr": 1e-3 * s}], lr=0.0, eps=1e-15)
+    pipe, bg = pipeline_params(), torch.zeros(3, device="cuda")
+    seen = 0
+    while seen < views_total:
+        for _ in range(views_per_step):
+            i = seen % len(cams)
+            (render(cams[i], pc, pipe, bg)["render"] - targets[i]).abs().mean().backward()   # .grad accumulates = the exchange's sum
+            seen += 1
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+    with torch.no_grad():
+        return float(np.mean([psnr(render(c, pc, pipe, bg)["render"], t) for c, t in zip(cams, targets)]))
+
+
+def test_view_parallel_steps_reach_the_serial_psnr_at_equal_views_seen():
+    """SURVEY.md section 8e caveat: the reference takes one optimizer step per view; N view-parallel ranks take one step per N views.
+    At the same number of views seen, 8-view steps (Adam is invariant to the gradient's scale, so the summed gradient needs no
+    rescaling; the step size is the one free parameter) must reach the serial run's PSNR."""
+    scene, pc, cams, pipe, bg = _scene(P=5000, seed=53, requires_grad=False)
+    with torch.no_grad():
+        targets = [render(c, pc, pipe, bg)["render"].clone() for c in cams]
+    rng = np.random.default_rng(1)
+    raw = {k: v.copy() for k, v in scene["raw"].items()}
+    raw["features_dc"] += 0.5 * rng.standard_normal(raw["features_dc"].shape).astype(np.float32)
+    raw["opacity"] += 1.0 * rng.standard_normal(raw["opacity"].shape).astype(np.float32)
+    start = GaussianParams(raw, 3, "cuda", requires_grad=False)
+    with torch.no_grad():
+        p0 = float(np.mean([psnr(render(c, start, pipe, bg)["render"], t) for c, t in zip(cams, targets)]))
+    views = 480
+    serial = _finetune_views_per_step(raw, cams, targets, 1, views, 1.0)
+    dp8_same_lr = _finetune_views_per_step(raw, cams, targets, 8, views, 1.0)
+    dp8 = _finetune_views_per_step(raw, cams, targets, 8, views, 4.0)     # 8x fewer steps, 4x the step size
+    assert serial > p0 + 3.0, (p0, serial)                                # the serial run learns something
+    assert dp8_same_lr > p0 + 1.0, (p0, dp8_same_lr)                      # so do 8-view steps, more slowly at the same step size
+    assert dp8 > serial - 0.03 * serial, (p0, serial, dp8_same_lr, dp8)   # and with the larger step they are within 3 % of the serial PSNR
