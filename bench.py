@@ -51,6 +51,8 @@ def parse_args():
     ap.add_argument("--blend-mode", type=int, default=0, help="DIAGNOSTIC: 0 = ring blend kernels (default), 1 = the round-1 blend kernels")
     ap.add_argument("--bin-mode", type=int, default=0, help="DIAGNOSTIC: 0 = hand-written binning, estimated blob size (default), 1 = exact blob "
                     "size (one stream sync), 2 = the round-1 library sorts")
+    ap.add_argument("--kback-mode", type=int, default=0, help="DIAGNOSTIC: fused K7+K8 of the raw backward: 0 = rows cleared inside the blend "
+                    "backward + compacted list (default), 1 = dense kernel, 2 = separate zero-fill kernel + compacted list")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -399,6 +401,7 @@ def main():
         capi.load()
         capi.set_blend_mode(args.blend_mode)
         capi.set_binning_mode(args.bin_mode)
+        capi.set_kback_mode(args.kback_mode)
         kind = None
     elif stock is not None:
         render_fn, kind = stock[0], "reference"

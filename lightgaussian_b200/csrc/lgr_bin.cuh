@@ -15,10 +15,11 @@
 //      scan     M[b][bin] <- sum over b' < b (exclusive, per bin); the last block to finish turns the bin totals into bin bases
 //               (and, for the tile pass, writes the per-tile ranges, the instance total and the capacity-overflow flag)
 //      scatter  block b re-reads its chunk IN ORDER; destination = base[bin] + M[b][bin] + (rank among the block's earlier items
-//               of that bin).  The rank comes from a shared-memory cursor per bin that the block's warps update in their input
-//               order: warps take turns (a shared ticket), inside a turn one __match_any_sync groups the 32 items of a step,
-//               the lowest lane of each group bumps the cursor and the others add their position in the group.  Loads, the
-//               instance generation and the global stores of different warps overlap; only the cursor update is serial.
+//               of that bin).  One __match_any_sync groups the 32 items of a step, the lowest lane of each group bumps a
+//               shared-memory counter and the others add their position in the group.  Depth sort (2048 bins): every warp owns a
+//               contiguous eighth of the chunk and a private row of 16-bit counters, no warp waits for another.  Tile pass (8160
+//               bins, one 32-bit cursor per tile): warps take turns row by row (a shared ticket); instance generation, loads and
+//               stores stay outside the turn.
 //
 // The instance count R is needed on the host only to size the binning blob.  The blob is sized from a running estimate BEFORE the
 // count is known; the kernels bound every store by that capacity and raise a flag when it is too small, the host looks at the
@@ -32,11 +33,13 @@ constexpr int BIN_V = 592;            // blocks of every count / scatter kernel 
 constexpr int DS_BITS = 11;
 constexpr int DS_BINS = 1 << DS_BITS;
 constexpr uint32_t BIN_NONE = 0xffffffffu;
-constexpr int TB_THREADS = 128;       // tile count / scatter block: 4 warps
+constexpr int TB_THREADS = 128;       // tile scatter block: 4 warps
+constexpr int TC_THREADS = 256;       // tile count block: 8 warps
+constexpr int TB_BUF = 512;           // instances of one 32-Gaussian row a scatter warp generates ahead of its turn
 constexpr int BIN_MAX_TILES = 49152;  // shared-memory cursor per tile (4 B): above this the library path is used
 
 __host__ __device__ inline int bin_pad(int bins) { return (bins + 255) / 256 * 256; }
-inline int bin_per_block(int P) { return ((P + BIN_V - 1) / BIN_V + 127) / 128 * 128; }
+inline int bin_per_block(int P) { return ((P + BIN_V - 1) / BIN_V + 255) / 256 * 256; }
 
 // header words at the start of the geometry blob
 enum { HDR_LISTED = 0, HDR_RENDERED = 1, HDR_CAPACITY = 2, HDR_OVERFLOW = 3, HDR_DONE = 8, HDR_LIVE = 9 };
@@ -164,59 +167,68 @@ __global__ void __launch_bounds__(256) bin_scan_kernel(BinScanArgs a)
     }
 }
 
-constexpr int DS_ITEMS = 4;   // keys per lane and turn: a warp ranks 128 consecutive keys per turn
-
+// Scatter of one depth-sort pass.  The block's chunk is cut into 8 contiguous sub-chunks, one per warp, so that "input order" inside the
+// block is (warp, position in the warp's sub-chunk) and no warp ever waits for another: pass A counts every warp's digits into ITS row of
+// a shared 8 x 2048 table of 16-bit counters (one __match_any_sync per 32 keys, the lowest lane of each group adds the group size),
+// a prefix over the 8 rows turns the counts into each warp's first slot per digit, pass B walks the sub-chunk again and hands out the
+// slots in order.  Keys are re-read from L1 in pass B.  per_block <= 65 535 keeps the counters in 16 bits.
 template <int SHIFT, bool FIRST, bool LAST>
 __global__ void __launch_bounds__(256) dsort_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ ids_in,
                                                             uint32_t* __restrict__ keys_out, uint32_t* __restrict__ ids_out,
                                                             const uint32_t* __restrict__ E, const uint32_t* __restrict__ bin_base, int P, int per_block)
 {
-    __shared__ uint32_t cursor[DS_BINS];
-    __shared__ int turn;
+    __shared__ uint16_t wcnt[8][DS_BINS];
+    __shared__ uint32_t base[DS_BINS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int i = threadIdx.x; i < DS_BINS; i += 256) cursor[i] = bin_base[i] + E[(size_t)blockIdx.x * DS_BINS + i];
-    if (threadIdx.x == 0) turn = 0;
+    {
+        uint32_t* z = reinterpret_cast<uint32_t*>(&wcnt[0][0]);
+        for (int i = threadIdx.x; i < 8 * DS_BINS / 2; i += 256) z[i] = 0u;
+        for (int i = threadIdx.x; i < DS_BINS; i += 256) base[i] = bin_base[i] + E[(size_t)blockIdx.x * DS_BINS + i];
+    }
     __syncthreads();
     const int lo = blockIdx.x * per_block, hi = min(P, lo + per_block);
-    const int nturns = (hi - lo + 32 * DS_ITEMS - 1) / (32 * DS_ITEMS);
+    const int per_warp = per_block / 8;   // per_block is a multiple of 256
+    const int wlo = lo + warp * per_warp, whi = min(hi, wlo + per_warp);
+    uint16_t* mine = wcnt[warp];
+    for (int k0 = wlo; k0 < whi; k0 += 32) {
+        const int k = k0 + lane;
+        const uint32_t d = k < whi ? ((keys_in[k] >> SHIFT) & (DS_BINS - 1)) : BIN_NONE;
+        const unsigned m = __match_any_sync(FULL, d);
+        if (d != BIN_NONE && lane == __ffs(m) - 1) mine[d] = (uint16_t)(mine[d] + __popc(m));
+        __syncwarp();
+    }
+    __syncthreads();
+    for (int d = threadIdx.x; d < DS_BINS; d += 256) {
+        uint32_t run = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) {
+            const uint32_t c = wcnt[w][d];
+            wcnt[w][d] = (uint16_t)run;
+            run += c;
+        }
+    }
+    __syncthreads();
     const unsigned lt = (1u << lane) - 1u;
-    for (int t = warp; t < nturns; t += 8) {
-        const int base = lo + t * 32 * DS_ITEMS;
-        uint32_t key[DS_ITEMS], id[DS_ITEMS], d[DS_ITEMS];
-        unsigned m[DS_ITEMS];
-#pragma unroll
-        for (int j = 0; j < DS_ITEMS; j++) {
-            const int k = base + j * 32 + lane;
-            const bool valid = k < hi;
-            key[j] = valid ? keys_in[k] : 0u;
-            id[j] = FIRST ? (uint32_t)k : (valid ? ids_in[k] : 0u);
-            d[j] = valid ? ((key[j] >> SHIFT) & (DS_BINS - 1)) : BIN_NONE;
-            m[j] = __match_any_sync(FULL, d[j]);
+    for (int k0 = wlo; k0 < whi; k0 += 32) {
+        const int k = k0 + lane;
+        const bool valid = k < whi;
+        const uint32_t key = valid ? keys_in[k] : 0u;
+        const uint32_t id = FIRST ? (uint32_t)k : (valid ? ids_in[k] : 0u);
+        const uint32_t d = valid ? ((key >> SHIFT) & (DS_BINS - 1)) : BIN_NONE;
+        const unsigned m = __match_any_sync(FULL, d);
+        const int leader = __ffs(m) - 1;
+        uint32_t old = 0;
+        if (valid && lane == leader) {
+            old = mine[d];
+            mine[d] = (uint16_t)(old + __popc(m));
         }
-        if (lane == 0)
-            while (*reinterpret_cast<volatile int*>(&turn) != t) {}
         __syncwarp();
-        uint32_t pos[DS_ITEMS];
-#pragma unroll
-        for (int j = 0; j < DS_ITEMS; j++) {
-            const int leader = __ffs(m[j]) - 1;
-            uint32_t old = 0;
-            if (lane == leader && d[j] != BIN_NONE) {
-                old = cursor[d[j]];
-                cursor[d[j]] = old + (uint32_t)__popc(m[j]);
-            }
-            __syncwarp();
-            pos[j] = __shfl_sync(FULL, old, leader) + (uint32_t)__popc(m[j] & lt);
+        old = __shfl_sync(FULL, old, leader);
+        if (valid) {
+            const uint32_t pos = base[d] + old + (uint32_t)__popc(m & lt);
+            if (!LAST) keys_out[pos] = key;
+            ids_out[pos] = id;
         }
-        __threadfence_block();
-        __syncwarp();
-        if (lane == 0) *reinterpret_cast<volatile int*>(&turn) = t + 1;
-#pragma unroll
-        for (int j = 0; j < DS_ITEMS; j++)
-            if (d[j] != BIN_NONE) {
-                if (!LAST) keys_out[pos[j]] = key[j];
-                ids_out[pos[j]] = id[j];
-            }
     }
 }
 
@@ -262,7 +274,7 @@ __device__ __forceinline__ void bin_row_load(const uint32_t* __restrict__ sorted
 }
 
 // instance j (row-local, j < r.total for valid lanes) -> tile index and owner id; BIN_NONE for lanes past the end
-__device__ __forceinline__ uint32_t bin_row_instance(const BinRow& r, uint32_t j, int gx, uint32_t& owner_id)
+__device__ __forceinline__ uint32_t bin_row_instance(const BinRow& r, uint32_t j, int gx, uint32_t& owner_id, int& owner_lane)
 {
     int lo = 0, hi = 31;   // largest lane m with off[m] <= j
 #pragma unroll
@@ -274,6 +286,7 @@ __device__ __forceinline__ uint32_t bin_row_instance(const BinRow& r, uint32_t j
     }
     const uint32_t o_off = __shfl_sync(FULL, r.off, lo);
     owner_id = __shfl_sync(FULL, r.id, lo);
+    owner_lane = lo;
     const int o_x0 = __shfl_sync(FULL, r.x0, lo), o_y0 = __shfl_sync(FULL, r.y0, lo), o_w = __shfl_sync(FULL, r.w, lo);
     const unsigned long long o_mask = __shfl_sync(FULL, r.mask, lo);
     if (j >= r.total) return BIN_NONE;
@@ -288,28 +301,29 @@ __device__ __forceinline__ uint32_t bin_row_instance(const BinRow& r, uint32_t j
     return (uint32_t)((o_y0 + ry) * gx + (o_x0 + rx));
 }
 
-__global__ void __launch_bounds__(TB_THREADS) tile_count_kernel(const uint32_t* __restrict__ sorted_ids, const uint4* __restrict__ bin_rec, int P,
+__global__ void __launch_bounds__(TC_THREADS) tile_count_kernel(const uint32_t* __restrict__ sorted_ids, const uint4* __restrict__ bin_rec, int P,
                                                                 int per_block, int gx, int tiles_pad, uint32_t* __restrict__ M, int* __restrict__ header)
 {
     extern __shared__ uint32_t tb_smem[];
     uint32_t* hist = tb_smem;
-    for (int i = threadIdx.x; i < tiles_pad; i += TB_THREADS) hist[i] = 0;
+    for (int i = threadIdx.x; i < tiles_pad; i += TC_THREADS) hist[i] = 0;
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int lo = blockIdx.x * per_block, hi = min(P, lo + per_block);
     uint32_t area = 0;
-    for (int row = lo + warp * 32; row < hi; row += (TB_THREADS / 32) * 32) {
+    for (int row = lo + warp * 32; row < hi; row += (TC_THREADS / 32) * 32) {
         BinRow r;
         bin_row_load(sorted_ids, bin_rec, row + lane, hi, lane, r);
         area += r.area;
         for (uint32_t base = 0; base < r.total; base += 32) {
             uint32_t owner;
-            const uint32_t tile = bin_row_instance(r, base + lane, gx, owner);
+            int olane;
+            const uint32_t tile = bin_row_instance(r, base + lane, gx, owner, olane);
             if (tile != BIN_NONE) atomicAdd(&hist[tile], 1u);
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < tiles_pad; i += TB_THREADS) M[(size_t)blockIdx.x * tiles_pad + i] = hist[i];
+    for (int i = threadIdx.x; i < tiles_pad; i += TC_THREADS) M[(size_t)blockIdx.x * tiles_pad + i] = hist[i];
     // the reference's num_rendered = sum of the rectangle areas (rasterizer_impl.cu:278-283)
     area = __reduce_add_sync(FULL, area);
     if (lane == 0 && area) atomicAdd(reinterpret_cast<unsigned*>(header + HDR_RENDERED), area);
@@ -320,8 +334,13 @@ __global__ void __launch_bounds__(TB_THREADS) tile_scatter_kernel(const uint32_t
                                                                   const uint32_t* __restrict__ bin_base, const int* __restrict__ header,
                                                                   uint32_t* __restrict__ point_list)
 {
+    // The cursor updates of a block must happen in depth order, i.e. row after row: warps take turns (a shared ticket).  Everything that
+    // does not touch the cursors happens OUTSIDE the turn: a warp loads its row and generates the row's instances (tile | owner lane << 16)
+    // into its own shared buffer while the other warps hold the ticket; inside the turn it only ranks: one shared load, one
+    // __match_any_sync, one cursor read-modify-write by the lowest lane of each group, two shuffles per 32 instances.
     extern __shared__ uint32_t tb_smem[];
     uint32_t* cursor = tb_smem;
+    __shared__ uint32_t gen[TB_THREADS / 32][TB_BUF];
     __shared__ int turn;
     for (int i = threadIdx.x; i < tiles_pad; i += TB_THREADS) cursor[i] = bin_base[i] + E[(size_t)blockIdx.x * tiles_pad + i];
     if (threadIdx.x == 0) turn = 0;
@@ -331,15 +350,42 @@ __global__ void __launch_bounds__(TB_THREADS) tile_scatter_kernel(const uint32_t
     const int lo = blockIdx.x * per_block, hi = min(P, lo + per_block);
     const int nrows = (hi - lo + 31) / 32;
     const unsigned lt = (1u << lane) - 1u;
+    uint32_t* buf = gen[warp];
     for (int t = warp; t < nrows; t += TB_THREADS / 32) {
         BinRow r;
         bin_row_load(sorted_ids, bin_rec, lo + t * 32 + lane, hi, lane, r);
-        if (lane == 0)
-            while (*reinterpret_cast<volatile int*>(&turn) != t) {}
+        const bool staged = r.total <= (uint32_t)TB_BUF;
+        if (staged) {
+            for (uint32_t base = 0; base < r.total; base += 32) {
+                uint32_t owner;
+                int olane;
+                const uint32_t tile = bin_row_instance(r, base + lane, gx, owner, olane);
+                if (tile != BIN_NONE) buf[base + lane] = tile | ((uint32_t)olane << 16);
+            }
+            __syncwarp();
+        }
+        if (lane == 0) {
+            unsigned ns = 32;
+            while (*reinterpret_cast<volatile int*>(&turn) != t) {
+                __nanosleep(ns);
+                if (ns < 256) ns *= 2;
+            }
+        }
         __syncwarp();
         for (uint32_t base = 0; base < r.total; base += 32) {
-            uint32_t owner;
-            const uint32_t tile = bin_row_instance(r, base + lane, gx, owner);
+            uint32_t tile = BIN_NONE, owner = 0;
+            if (staged) {
+                int olane = 0;
+                if (base + lane < r.total) {
+                    const uint32_t v = buf[base + lane];
+                    tile = v & 0xffffu;
+                    olane = (int)(v >> 16);
+                }
+                owner = __shfl_sync(FULL, r.id, olane);
+            } else {   // a row of screen-filling splats: generate inside the turn
+                int olane;
+                tile = bin_row_instance(r, base + lane, gx, owner, olane);
+            }
             const unsigned m = __match_any_sync(FULL, tile);
             const int leader = __ffs(m) - 1;
             uint32_t old = 0;

@@ -1169,7 +1169,7 @@ int forward_impl(const lgr_view* v, int P, int M, const float* means3D, const fl
         return LGR_ERR_INVALID_ARG;
     }
     const int tiles = gx * gy;
-    const bool lib_bin = g_bin_mode == 2 || tiles > BIN_MAX_TILES || gx > 0xffff || gy > 0xffff;
+    const bool lib_bin = g_bin_mode == 2 || tiles > BIN_MAX_TILES || gx > 0xffff || gy > 0xffff || bin_per_block(P) > 65535;
     GeometryState geo = carve_geometry(nullptr, (size_t)P, lib_bin);
     char* geo_blob = geometry_alloc(geometry_user, geo.total);
     if (!geo_blob) { g_last_error = "geometry allocator returned NULL"; return LGR_ERR_ALLOC; }
@@ -1278,7 +1278,7 @@ int forward_impl(const lgr_view* v, int P, int M, const float* means3D, const fl
         }
         {
             ProfScope ps(ST_BIN_COUNT, stream);
-            tile_count_kernel<<<BIN_V, TB_THREADS, tb_smem, stream>>>(geo.sorted_ids, geo.bin_rec, P, per_block, gx, tiles_pad, img.bin_M, geo.num_rendered);
+            tile_count_kernel<<<BIN_V, TC_THREADS, tb_smem, stream>>>(geo.sorted_ids, geo.bin_rec, P, per_block, gx, tiles_pad, img.bin_M, geo.num_rendered);
             BinScanArgs sa;
             sa.M = img.bin_M; sa.V = BIN_V; sa.bins = tiles; sa.bins_pad = tiles_pad; sa.bin_total = img.bin_total; sa.bin_base = img.bin_base;
             sa.header = geo.num_rendered; sa.ranges = img.ranges;
@@ -1731,8 +1731,8 @@ int lgr_backward_raw_end_range(const lgr_view* v, int P, int M, const lgr_raw_pa
         else kback_zero_flag_kernel<true><<<(P + 255) / 256, 256, 0, stream>>>(z);
         LGR_LAUNCH_CHECK("kback_zero_flag_kernel", debug, stream);
         a.P = P;
-        const int blocks = std::min((P + 255) / 256, 148 * 8);
-        preprocess_backward_compact_kernel<<<blocks, 256, 0, stream>>>(a, reinterpret_cast<const int*>(geo.sorted_ids), counter);
+        const int blocks = std::min((P + KC_THREADS - 1) / KC_THREADS, 148 * 8);
+        preprocess_backward_compact_kernel<<<blocks, KC_THREADS, 0, stream>>>(a, reinterpret_cast<const int*>(geo.sorted_ids), counter);
         LGR_LAUNCH_CHECK("preprocess_backward_compact_kernel", debug, stream);
         return LGR_OK;
     }
