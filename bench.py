@@ -419,7 +419,21 @@ def main():
     elif stock is not None:
         step_loss = stock[2]        # utils/loss_utils.py:18-19, the reference's own
 
+    # which view a rank renders in a step.  N > 1: a step lasts as long as its slowest rank, so the views of one step are chosen with
+    # similar cost (parallel.balanced_view_schedule on each camera's instance count, measured here by every rank for all cameras ->
+    # the same schedule everywhere without communication); every camera is still used equally often.
+    schedule = None
+    if world > 1 and args.impl == "ours" and os.environ.get("LGR_BALANCED_VIEWS", "1") != "0":
+        costs = []
+        with torch.no_grad():
+            for c in cams:
+                render_fn(c, pc, pipe, bg)
+                costs.append(rasterizer.last_num_rendered())
+        schedule = parallel.balanced_view_schedule(costs, world)
+
     def view_index(step):
+        if schedule is not None:
+            return schedule[step % len(schedule)][rank]
         return (step * world + rank) % len(cams)
 
     def step_resident(step):

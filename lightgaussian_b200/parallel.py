@@ -36,6 +36,23 @@ def shard_views(n_views: int, rank: int, world: int) -> List[int]:
     return list(range(rank, n_views, world))
 
 
+def balanced_view_schedule(costs: Sequence[float], world: int) -> List[List[int]]:
+    """Steps of `world` views each with SIMILAR cost inside a step.  A view-parallel step lasts as long as its slowest rank, so the views
+    of one step should cost the same: views are ordered by cost (e.g. the instance count `num_rendered` of the previous epoch) and cut
+    into consecutive groups of `world`; group g is step g, its k-th view goes to rank (k + g) mod world so that no rank always gets the
+    heavier end of its groups.  Every view appears exactly once; a last incomplete group is padded by repeating its own views.
+    Deterministic in `costs`, so all ranks compute the same schedule without talking to each other.  Returns schedule[step][rank]."""
+    order = sorted(range(len(costs)), key=lambda i: (-float(costs[i]), i))
+    steps = []
+    for g in range(0, len(order), world):
+        grp = order[g:g + world]
+        while len(grp) < world:
+            grp = grp + grp[:world - len(grp)]
+        r = (g // world) % world
+        steps.append([grp[(k - r) % world] for k in range(world)])
+    return steps
+
+
 class FlatGrads:
     """One contiguous fp32 buffer holding every parameter's gradient, with `.grad` of each parameter a view into
     it, so the per-step exchange is a single NCCL all-reduce over NVLink instead of one per tensor."""

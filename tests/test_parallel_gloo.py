@@ -78,3 +78,23 @@ def test_flat_grads_views_alias_the_buffer():
     assert torch.equal(flat.flat, torch.cat([torch.full((12,), 2.0), torch.full((6,), 3.0)]))
     flat.zero()
     assert params[0].grad.abs().sum() == 0 and flat.nbytes == 18 * 4
+
+
+def test_balanced_view_schedule_groups_views_of_similar_cost():
+    g = torch.Generator().manual_seed(3)
+    costs = (torch.rand(16, generator=g) * 10 + 5).tolist()
+    for world in (2, 4, 8):
+        sched = parallel.balanced_view_schedule(costs, world)
+        assert sorted(i for step in sched for i in step) == list(range(16))          # every view exactly once
+        assert all(len(step) == world for step in sched)
+        spread = max(max(costs[i] for i in s) - min(costs[i] for i in s) for s in sched)
+        naive = max(max(costs[(t * world + r) % 16] for r in range(world)) - min(costs[(t * world + r) % 16] for r in range(world))
+                    for t in range(16 // world))
+        assert spread <= naive
+        # the slowest rank of every step, summed: never worse than the round-robin assignment
+        assert sum(max(costs[i] for i in s) for s in sched) <= sum(max(costs[(t * world + r) % 16] for r in range(world))
+                                                                   for t in range(16 // world)) + 1e-9
+    # an incomplete last group repeats its own views; no rank is left without work
+    sched = parallel.balanced_view_schedule([3.0, 1.0, 2.0, 5.0, 4.0], 4)
+    assert len(sched) == 2 and all(len(s) == 4 for s in sched) and set(sched[1]) == {1}
+    assert parallel.balanced_view_schedule(costs, 2) == parallel.balanced_view_schedule(list(costs), 2)   # deterministic
