@@ -6,7 +6,7 @@
 //
 //   1. depth order of the P Gaussians: LSD radix sort of the 32-bit depth keys in THREE passes of 11 / 11 / 10 bits (the library
 //      sort took four 8-bit passes), ids implicit in the first pass, keys dropped in the last.
-//   2. tile bucketing: ONE stable counting-sort pass over the (up to 50 000) tile indices.  Instances are never materialised
+//   2. tile bucketing: ONE stable counting-sort pass over the (up to 32 768) tile indices.  Instances are never materialised
 //      unsorted: a count kernel and a scatter kernel both regenerate them from the 16-byte per-Gaussian bin record
 //      (tile rectangle + exact 64-bit keep mask, written by the preprocess kernel) walking the Gaussians in depth order.
 //
@@ -15,11 +15,14 @@
 //      scan     M[b][bin] <- sum over b' < b (exclusive, per bin); the last block to finish turns the bin totals into bin bases
 //               (and, for the tile pass, writes the per-tile ranges, the instance total and the capacity-overflow flag)
 //      scatter  block b re-reads its chunk IN ORDER; destination = base[bin] + M[b][bin] + (rank among the block's earlier items
-//               of that bin).  One __match_any_sync groups the 32 items of a step, the lowest lane of each group bumps a
-//               shared-memory counter and the others add their position in the group.  Depth sort (2048 bins): every warp owns a
-//               contiguous eighth of the chunk and a private row of 16-bit counters, no warp waits for another.  Tile pass (8160
-//               bins, one 32-bit cursor per tile): warps take turns row by row (a shared ticket); instance generation, loads and
-//               stores stay outside the turn.
+//               of that bin).  Items are ranked 32 at a time: lanes holding the same bin are found with one ballot per key bit
+//               (warp_match: cost = number of bits, where __match_any_sync costs one round per DISTINCT value -- measured 10x
+//               slower on these mostly-distinct keys), the lowest lane of each group bumps a shared-memory counter, the others
+//               add their position in the group.  Depth sort (2048 bins): every warp owns a contiguous eighth of the chunk and
+//               a private row of 16-bit counters, no warp waits for another.  Tile pass (8160 bins, one 32-bit cursor per tile):
+//               the cursor updates of a block must follow the depth order, so warps take turns row by row (a shared ticket);
+//               loads, instance generation and the group masks are computed before the turn, inside it a step is one shared load,
+//               one cursor read-modify-write and a shuffle.
 //
 // The instance count R is needed on the host only to size the binning blob.  The blob is sized from a running estimate BEFORE the
 // count is known; the kernels bound every store by that capacity and raise a flag when it is too small, the host looks at the
@@ -33,16 +36,34 @@ constexpr int BIN_V = 592;            // blocks of every count / scatter kernel 
 constexpr int DS_BITS = 11;
 constexpr int DS_BINS = 1 << DS_BITS;
 constexpr uint32_t BIN_NONE = 0xffffffffu;
-constexpr int TB_THREADS = 128;       // tile scatter block: 4 warps
+constexpr int TB_THREADS = 256;       // tile scatter block: 8 warps
 constexpr int TC_THREADS = 256;       // tile count block: 8 warps
-constexpr int TB_BUF = 512;           // instances of one 32-Gaussian row a scatter warp generates ahead of its turn
-constexpr int BIN_MAX_TILES = 49152;  // shared-memory cursor per tile (4 B): above this the library path is used
+constexpr int TB_BUF = 256;           // instances of one 32-Gaussian row a scatter warp prepares ahead of its turn
+constexpr int SCAN_THREADS = 512;     // scan block: 16 warps share the rows of a 32-bin strip
+constexpr int SCAN_ROWS = 40;         // rows per scan warp held in registers: BIN_V <= 16 * 40
+constexpr int BIN_MAX_TILES = 32768;  // shared-memory cursor per tile (4 B) + staging: above this the library path is used
+
+static_assert(BIN_V <= (SCAN_THREADS / 32) * SCAN_ROWS, "scan kernel: too many matrix rows");
 
 __host__ __device__ inline int bin_pad(int bins) { return (bins + 255) / 256 * 256; }
 inline int bin_per_block(int P) { return ((P + BIN_V - 1) / BIN_V + 255) / 256 * 256; }
 
 // header words at the start of the geometry blob
 enum { HDR_LISTED = 0, HDR_RENDERED = 1, HDR_CAPACITY = 2, HDR_OVERFLOW = 3, HDR_DONE = 8, HDR_LIVE = 9 };
+
+// lanes with the same key (and valid) get the same mask of lanes; invalid lanes get 0.  One ballot per key bit.
+template <int BITS>
+__device__ __forceinline__ unsigned warp_match(uint32_t key, bool valid)
+{
+    unsigned m = __ballot_sync(FULL, valid);
+#pragma unroll
+    for (int b = 0; b < BITS; b++) {
+        const bool bit = (key >> b) & 1u;
+        const unsigned bal = __ballot_sync(FULL, bit);
+        m &= bit ? bal : ~bal;
+    }
+    return valid ? m : 0u;
+}
 
 // ------------------------------------------------------------------------------------------------
 // depth sort: one LSD pass = count -> scan -> scatter
@@ -55,13 +76,13 @@ __global__ void __launch_bounds__(256) dsort_count_kernel(const uint32_t* __rest
     for (int i = threadIdx.x; i < DS_BINS; i += 256) hist[i] = 0;
     if (FIRST && blockIdx.x == 0 && threadIdx.x < 16) header[threadIdx.x] = 0;
     __syncthreads();
-    const int lo = blockIdx.x * per_block, hi = min(P, lo + per_block);
-    const int lane = threadIdx.x & 31;
-    for (int k0 = lo + (threadIdx.x & ~31); k0 < hi; k0 += 256) {
-        const int k = k0 + lane;
-        const uint32_t d = k < hi ? ((keys[k] >> SHIFT) & (DS_BINS - 1)) : BIN_NONE;
-        const unsigned m = __match_any_sync(FULL, d);   // the top pass has a handful of distinct digits: aggregate per warp
-        if (d != BIN_NONE && lane == __ffs(m) - 1) atomicAdd(&hist[d], (uint32_t)__popc(m));
+    const int lo = blockIdx.x * per_block, hi = min(P, lo + per_block);   // lo is a multiple of 256: 16-byte aligned key quads
+    for (int k = lo + 4 * (int)threadIdx.x; k < hi; k += 4 * 256) {
+        const uint4 q = *reinterpret_cast<const uint4*>(keys + k);   // may read past hi, still inside the blob; masked below
+        atomicAdd(&hist[(q.x >> SHIFT) & (DS_BINS - 1)], 1u);
+        if (k + 1 < hi) atomicAdd(&hist[(q.y >> SHIFT) & (DS_BINS - 1)], 1u);
+        if (k + 2 < hi) atomicAdd(&hist[(q.z >> SHIFT) & (DS_BINS - 1)], 1u);
+        if (k + 3 < hi) atomicAdd(&hist[(q.w >> SHIFT) & (DS_BINS - 1)], 1u);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < DS_BINS; i += 256) M[(size_t)blockIdx.x * DS_BINS + i] = hist[i];
@@ -78,55 +99,38 @@ struct BinScanArgs {
 };
 
 template <bool TILES>
-__global__ void __launch_bounds__(256) bin_scan_kernel(BinScanArgs a)
+__global__ void __launch_bounds__(SCAN_THREADS) bin_scan_kernel(BinScanArgs a)
 {
-    __shared__ uint32_t part[8][32];
-    __shared__ uint32_t wsum[8];
+    constexpr int NW = SCAN_THREADS / 32;
+    __shared__ uint32_t part[NW][32];
+    __shared__ uint32_t wsum[NW];
     __shared__ bool last;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int bin = blockIdx.x * 32 + lane;   // gridDim.x = bins_pad / 32
-    const int rows_per = (a.V + 7) / 8;
+    const int rows_per = (a.V + NW - 1) / NW;  // <= SCAN_ROWS
     const int r0 = warp * rows_per, r1 = min(a.V, r0 + rows_per);
     uint32_t* col = a.M + bin;
     const size_t stride = (size_t)a.bins_pad;
+    // the warp's rows of this 32-bin strip: every load in flight at once, the prefix runs over registers
+    uint32_t v[SCAN_ROWS];
+#pragma unroll
+    for (int u = 0; u < SCAN_ROWS; u++) v[u] = (r0 + u < r1) ? col[(size_t)(r0 + u) * stride] : 0u;
     uint32_t s = 0;
-    {
-        int r = r0;
-        for (; r + 8 <= r1; r += 8) {
-            uint32_t v[8];
 #pragma unroll
-            for (int u = 0; u < 8; u++) v[u] = col[(size_t)(r + u) * stride];
-#pragma unroll
-            for (int u = 0; u < 8; u++) s += v[u];
-        }
-        for (; r < r1; r++) s += col[(size_t)r * stride];
-    }
+    for (int u = 0; u < SCAN_ROWS; u++) s += v[u];
     part[warp][lane] = s;
     __syncthreads();
     uint32_t run = 0, total = 0;
 #pragma unroll
-    for (int w = 0; w < 8; w++) {
-        const uint32_t v = part[w][lane];
-        if (w < warp) run += v;
-        total += v;
+    for (int w = 0; w < NW; w++) {
+        const uint32_t c = part[w][lane];
+        if (w < warp) run += c;
+        total += c;
     }
-    {
-        int r = r0;
-        for (; r + 8 <= r1; r += 8) {
-            uint32_t v[8];
 #pragma unroll
-            for (int u = 0; u < 8; u++) v[u] = col[(size_t)(r + u) * stride];
-#pragma unroll
-            for (int u = 0; u < 8; u++) {
-                col[(size_t)(r + u) * stride] = run;
-                run += v[u];
-            }
-        }
-        for (; r < r1; r++) {
-            const uint32_t v = col[(size_t)r * stride];
-            col[(size_t)r * stride] = run;
-            run += v;
-        }
+    for (int u = 0; u < SCAN_ROWS; u++) {
+        if (r0 + u < r1) col[(size_t)(r0 + u) * stride] = run;
+        run += v[u];
     }
     if (warp == 0) a.bin_total[bin] = total;
 
@@ -137,10 +141,11 @@ __global__ void __launch_bounds__(256) bin_scan_kernel(BinScanArgs a)
     __syncthreads();
     if (!last) return;
     __threadfence();
-    const int chunk = a.bins_pad / 256;   // consecutive bins per thread
+    const int chunk = a.bins_pad / 256;   // consecutive bins per thread (threads 0..255)
     const int c0 = threadIdx.x * chunk;
     uint32_t mine = 0;
-    for (int i = 0; i < chunk; i++) mine += __ldcg(a.bin_total + c0 + i);
+    if (threadIdx.x < 256)
+        for (int i = 0; i < chunk; i++) mine += __ldcg(a.bin_total + c0 + i);
     uint32_t incl = mine;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -149,6 +154,7 @@ __global__ void __launch_bounds__(256) bin_scan_kernel(BinScanArgs a)
     }
     if (lane == 31) wsum[warp] = incl;
     __syncthreads();
+    if (threadIdx.x >= 256) return;
     uint32_t base = incl - mine;
     for (int w = 0; w < warp; w++) base += wsum[w];
     for (int i = 0; i < chunk; i++) {
@@ -169,14 +175,17 @@ __global__ void __launch_bounds__(256) bin_scan_kernel(BinScanArgs a)
 
 // Scatter of one depth-sort pass.  The block's chunk is cut into 8 contiguous sub-chunks, one per warp, so that "input order" inside the
 // block is (warp, position in the warp's sub-chunk) and no warp ever waits for another: pass A counts every warp's digits into ITS row of
-// a shared 8 x 2048 table of 16-bit counters (one __match_any_sync per 32 keys, the lowest lane of each group adds the group size),
-// a prefix over the 8 rows turns the counts into each warp's first slot per digit, pass B walks the sub-chunk again and hands out the
-// slots in order.  Keys are re-read from L1 in pass B.  per_block <= 65 535 keeps the counters in 16 bits.
+// a shared 8 x 2048 table of 16-bit counters, a prefix over the 8 rows turns the counts into each warp's first slot per digit, pass B
+// walks the sub-chunk again and hands out the slots in order.  Keys are fetched four steps ahead (and come from L1 in pass B).
+// per_block <= 65 535 keeps the counters in 16 bits.
+constexpr int DS_AHEAD = 4;
+
 template <int SHIFT, bool FIRST, bool LAST>
 __global__ void __launch_bounds__(256) dsort_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ ids_in,
                                                             uint32_t* __restrict__ keys_out, uint32_t* __restrict__ ids_out,
                                                             const uint32_t* __restrict__ E, const uint32_t* __restrict__ bin_base, int P, int per_block)
 {
+    constexpr int BITS = (32 - SHIFT) < DS_BITS ? (32 - SHIFT) : DS_BITS;
     __shared__ uint16_t wcnt[8][DS_BINS];
     __shared__ uint32_t base[DS_BINS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -190,12 +199,21 @@ __global__ void __launch_bounds__(256) dsort_scatter_kernel(const uint32_t* __re
     const int per_warp = per_block / 8;   // per_block is a multiple of 256
     const int wlo = lo + warp * per_warp, whi = min(hi, wlo + per_warp);
     uint16_t* mine = wcnt[warp];
-    for (int k0 = wlo; k0 < whi; k0 += 32) {
-        const int k = k0 + lane;
-        const uint32_t d = k < whi ? ((keys_in[k] >> SHIFT) & (DS_BINS - 1)) : BIN_NONE;
-        const unsigned m = __match_any_sync(FULL, d);
-        if (d != BIN_NONE && lane == __ffs(m) - 1) mine[d] = (uint16_t)(mine[d] + __popc(m));
-        __syncwarp();
+    for (int k0 = wlo; k0 < whi; k0 += 32 * DS_AHEAD) {
+        uint32_t key[DS_AHEAD];
+#pragma unroll
+        for (int j = 0; j < DS_AHEAD; j++) {
+            const int k = k0 + 32 * j + lane;
+            key[j] = k < whi ? keys_in[k] : 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < DS_AHEAD; j++) {
+            const bool valid = k0 + 32 * j + lane < whi;
+            const uint32_t d = (key[j] >> SHIFT) & (DS_BINS - 1);
+            const unsigned m = warp_match<BITS>(d, valid);
+            if (valid && lane == __ffs(m) - 1) mine[d] = (uint16_t)(mine[d] + __popc(m));
+            __syncwarp();
+        }
     }
     __syncthreads();
     for (int d = threadIdx.x; d < DS_BINS; d += 256) {
@@ -209,25 +227,33 @@ __global__ void __launch_bounds__(256) dsort_scatter_kernel(const uint32_t* __re
     }
     __syncthreads();
     const unsigned lt = (1u << lane) - 1u;
-    for (int k0 = wlo; k0 < whi; k0 += 32) {
-        const int k = k0 + lane;
-        const bool valid = k < whi;
-        const uint32_t key = valid ? keys_in[k] : 0u;
-        const uint32_t id = FIRST ? (uint32_t)k : (valid ? ids_in[k] : 0u);
-        const uint32_t d = valid ? ((key >> SHIFT) & (DS_BINS - 1)) : BIN_NONE;
-        const unsigned m = __match_any_sync(FULL, d);
-        const int leader = __ffs(m) - 1;
-        uint32_t old = 0;
-        if (valid && lane == leader) {
-            old = mine[d];
-            mine[d] = (uint16_t)(old + __popc(m));
+    for (int k0 = wlo; k0 < whi; k0 += 32 * DS_AHEAD) {
+        uint32_t key[DS_AHEAD], id[DS_AHEAD];
+#pragma unroll
+        for (int j = 0; j < DS_AHEAD; j++) {
+            const int k = k0 + 32 * j + lane;
+            const bool valid = k < whi;
+            key[j] = valid ? keys_in[k] : 0u;
+            id[j] = FIRST ? (uint32_t)k : (valid ? ids_in[k] : 0u);
         }
-        __syncwarp();
-        old = __shfl_sync(FULL, old, leader);
-        if (valid) {
-            const uint32_t pos = base[d] + old + (uint32_t)__popc(m & lt);
-            if (!LAST) keys_out[pos] = key;
-            ids_out[pos] = id;
+#pragma unroll
+        for (int j = 0; j < DS_AHEAD; j++) {
+            const bool valid = k0 + 32 * j + lane < whi;
+            const uint32_t d = (key[j] >> SHIFT) & (DS_BINS - 1);
+            const unsigned m = warp_match<BITS>(d, valid);
+            const int leader = __ffs(m) - 1;
+            uint32_t old = 0;
+            if (valid && lane == leader) {
+                old = mine[d];
+                mine[d] = (uint16_t)(old + __popc(m));
+            }
+            __syncwarp();
+            old = __shfl_sync(FULL, old, leader & 31);
+            if (valid) {
+                const uint32_t pos = base[d] + old + (uint32_t)__popc(m & lt);
+                if (!LAST) keys_out[pos] = key[j];
+                ids_out[pos] = id[j];
+            }
         }
     }
 }
@@ -243,25 +269,39 @@ __device__ __forceinline__ uint4 make_bin_rec(int x0, int y0, int w, int h, unsi
     return make_uint4((uint32_t)x0 | ((uint32_t)y0 << 16), (uint32_t)w | ((uint32_t)h << 16), (uint32_t)mask, (uint32_t)(mask >> 32));
 }
 
-struct BinRow {   // one lane's Gaussian of a 32-Gaussian row
+struct BinRowRaw {   // one lane's Gaussian of a 32-Gaussian row, as loaded
+    uint32_t id;
+    uint4 rec;
+};
+
+struct BinRow {   // ... and decoded
     uint32_t id, cnt, off, total, area;
     int x0, y0, w;
     unsigned long long mask;
 };
 
-__device__ __forceinline__ void bin_row_load(const uint32_t* __restrict__ sorted_ids, const uint4* __restrict__ bin_rec, int k, int kend, int lane, BinRow& r)
+__device__ __forceinline__ BinRowRaw bin_row_fetch(const uint32_t* __restrict__ sorted_ids, const uint4* __restrict__ bin_rec, int k, int kend)
 {
-    r.id = 0; r.cnt = 0; r.area = 0; r.x0 = 0; r.y0 = 0; r.w = 1; r.mask = ~0ull;
+    BinRowRaw r;
+    r.id = 0;
+    r.rec = make_uint4(0u, 0u, 0u, 0u);
     if (k < kend) {
         r.id = sorted_ids[k];
-        const uint4 q = __ldg(bin_rec + r.id);
-        const int w = (int)(q.y & 0xffffu), h = (int)(q.y >> 16);
-        r.area = (uint32_t)(w * h);
-        if (r.area) {
-            r.x0 = (int)(q.x & 0xffffu); r.y0 = (int)(q.x >> 16); r.w = w;
-            r.mask = (unsigned long long)q.z | ((unsigned long long)q.w << 32);
-            r.cnt = r.area > 64u ? r.area : (uint32_t)__popcll(r.mask);
-        }
+        r.rec = __ldg(bin_rec + r.id);
+    }
+    return r;
+}
+
+__device__ __forceinline__ void bin_row_decode(const BinRowRaw& in, int lane, BinRow& r)
+{
+    r.id = in.id; r.cnt = 0; r.x0 = 0; r.y0 = 0; r.w = 1; r.mask = ~0ull;
+    const uint4 q = in.rec;
+    const int w = (int)(q.y & 0xffffu), h = (int)(q.y >> 16);
+    r.area = (uint32_t)(w * h);
+    if (r.area) {
+        r.x0 = (int)(q.x & 0xffffu); r.y0 = (int)(q.x >> 16); r.w = w;
+        r.mask = (unsigned long long)q.z | ((unsigned long long)q.w << 32);
+        r.cnt = r.area > 64u ? r.area : (uint32_t)__popcll(r.mask);
     }
     uint32_t incl = r.cnt;
 #pragma unroll
@@ -273,7 +313,7 @@ __device__ __forceinline__ void bin_row_load(const uint32_t* __restrict__ sorted
     r.total = __shfl_sync(FULL, incl, 31);
 }
 
-// instance j (row-local, j < r.total for valid lanes) -> tile index and owner id; BIN_NONE for lanes past the end
+// instance j (row-local, j < r.total for valid lanes) -> tile index, owner id and owner lane; BIN_NONE for lanes past the end
 __device__ __forceinline__ uint32_t bin_row_instance(const BinRow& r, uint32_t j, int gx, uint32_t& owner_id, int& owner_lane)
 {
     int lo = 0, hi = 31;   // largest lane m with off[m] <= j
@@ -310,10 +350,15 @@ __global__ void __launch_bounds__(TC_THREADS) tile_count_kernel(const uint32_t* 
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int lo = blockIdx.x * per_block, hi = min(P, lo + per_block);
+    constexpr int STEP = (TC_THREADS / 32) * 32;
     uint32_t area = 0;
-    for (int row = lo + warp * 32; row < hi; row += (TC_THREADS / 32) * 32) {
+    int row = lo + warp * 32;
+    BinRowRaw next = bin_row_fetch(sorted_ids, bin_rec, row + lane, hi);
+    for (; row < hi; row += STEP) {
+        const BinRowRaw cur = next;
+        next = bin_row_fetch(sorted_ids, bin_rec, row + STEP + lane, hi);   // the next row's loads fly while this one is expanded
         BinRow r;
-        bin_row_load(sorted_ids, bin_rec, row + lane, hi, lane, r);
+        bin_row_decode(cur, lane, r);
         area += r.area;
         for (uint32_t base = 0; base < r.total; base += 32) {
             uint32_t owner;
@@ -329,18 +374,19 @@ __global__ void __launch_bounds__(TC_THREADS) tile_count_kernel(const uint32_t* 
     if (lane == 0 && area) atomicAdd(reinterpret_cast<unsigned*>(header + HDR_RENDERED), area);
 }
 
+inline size_t tile_scatter_smem(int tiles_pad) { return sizeof(uint32_t) * (size_t)tiles_pad + sizeof(uint2) * (size_t)(TB_THREADS / 32) * TB_BUF; }
+
 __global__ void __launch_bounds__(TB_THREADS) tile_scatter_kernel(const uint32_t* __restrict__ sorted_ids, const uint4* __restrict__ bin_rec, int P,
                                                                   int per_block, int gx, int tiles_pad, const uint32_t* __restrict__ E,
                                                                   const uint32_t* __restrict__ bin_base, const int* __restrict__ header,
                                                                   uint32_t* __restrict__ point_list)
 {
-    // The cursor updates of a block must happen in depth order, i.e. row after row: warps take turns (a shared ticket).  Everything that
-    // does not touch the cursors happens OUTSIDE the turn: a warp loads its row and generates the row's instances (tile | owner lane << 16)
-    // into its own shared buffer while the other warps hold the ticket; inside the turn it only ranks: one shared load, one
-    // __match_any_sync, one cursor read-modify-write by the lowest lane of each group, two shuffles per 32 instances.
+    // Ahead of its turn a warp loads its row (the next row's loads are already in flight), generates the row's instances and groups the
+    // 32 instances of every step by tile (warp_match); per instance it parks {tile | owner lane << 16, group mask} in its shared buffer.
+    // Inside the turn a step is: one 64-bit shared load, the group's lowest lane reads and bumps the tile's cursor, one shuffle.
     extern __shared__ uint32_t tb_smem[];
-    uint32_t* cursor = tb_smem;
-    __shared__ uint32_t gen[TB_THREADS / 32][TB_BUF];
+    uint32_t* cursor = tb_smem;                                      // [tiles_pad]
+    uint2* gen = reinterpret_cast<uint2*>(tb_smem + tiles_pad);      // [warps][TB_BUF]
     __shared__ int turn;
     for (int i = threadIdx.x; i < tiles_pad; i += TB_THREADS) cursor[i] = bin_base[i] + E[(size_t)blockIdx.x * tiles_pad + i];
     if (threadIdx.x == 0) turn = 0;
@@ -350,56 +396,58 @@ __global__ void __launch_bounds__(TB_THREADS) tile_scatter_kernel(const uint32_t
     const int lo = blockIdx.x * per_block, hi = min(P, lo + per_block);
     const int nrows = (hi - lo + 31) / 32;
     const unsigned lt = (1u << lane) - 1u;
-    uint32_t* buf = gen[warp];
-    for (int t = warp; t < nrows; t += TB_THREADS / 32) {
+    constexpr int NW = TB_THREADS / 32;
+    uint2* buf = gen + warp * TB_BUF;
+    volatile int* vturn = &turn;
+    BinRowRaw next = bin_row_fetch(sorted_ids, bin_rec, lo + warp * 32 + lane, hi);
+    for (int t = warp; t < nrows; t += NW) {
+        const BinRowRaw cur = next;
+        next = bin_row_fetch(sorted_ids, bin_rec, lo + (t + NW) * 32 + lane, hi);
         BinRow r;
-        bin_row_load(sorted_ids, bin_rec, lo + t * 32 + lane, hi, lane, r);
+        bin_row_decode(cur, lane, r);
         const bool staged = r.total <= (uint32_t)TB_BUF;
         if (staged) {
             for (uint32_t base = 0; base < r.total; base += 32) {
                 uint32_t owner;
                 int olane;
                 const uint32_t tile = bin_row_instance(r, base + lane, gx, owner, olane);
-                if (tile != BIN_NONE) buf[base + lane] = tile | ((uint32_t)olane << 16);
+                const unsigned m = warp_match<16>(tile, tile != BIN_NONE);
+                if (tile != BIN_NONE) buf[base + lane] = make_uint2(tile | ((uint32_t)olane << 16), m);
             }
             __syncwarp();
         }
-        if (lane == 0) {
-            unsigned ns = 32;
-            while (*reinterpret_cast<volatile int*>(&turn) != t) {
-                __nanosleep(ns);
-                if (ns < 256) ns *= 2;
-            }
-        }
+        if (lane == 0)
+            while (*vturn != t) {}
         __syncwarp();
         for (uint32_t base = 0; base < r.total; base += 32) {
             uint32_t tile = BIN_NONE, owner = 0;
+            unsigned m = 0;
             if (staged) {
                 int olane = 0;
                 if (base + lane < r.total) {
-                    const uint32_t v = buf[base + lane];
-                    tile = v & 0xffffu;
-                    olane = (int)(v >> 16);
+                    const uint2 v = buf[base + lane];
+                    tile = v.x & 0xffffu;
+                    olane = (int)(v.x >> 16);
+                    m = v.y;
                 }
                 owner = __shfl_sync(FULL, r.id, olane);
             } else {   // a row of screen-filling splats: generate inside the turn
                 int olane;
                 tile = bin_row_instance(r, base + lane, gx, owner, olane);
+                m = warp_match<16>(tile, tile != BIN_NONE);
             }
-            const unsigned m = __match_any_sync(FULL, tile);
             const int leader = __ffs(m) - 1;
             uint32_t old = 0;
-            if (lane == leader && tile != BIN_NONE) {
+            if (tile != BIN_NONE && lane == leader) {
                 old = cursor[tile];
                 cursor[tile] = old + (uint32_t)__popc(m);
             }
             __syncwarp();
-            const uint32_t pos = __shfl_sync(FULL, old, leader) + (uint32_t)__popc(m & lt);
+            const uint32_t pos = __shfl_sync(FULL, old, leader & 31) + (uint32_t)__popc(m & lt);
             if (tile != BIN_NONE && pos < capacity) point_list[pos] = owner;
         }
-        __threadfence_block();
         __syncwarp();
-        if (lane == 0) *reinterpret_cast<volatile int*>(&turn) = t + 1;
+        if (lane == 0) *vturn = t + 1;
     }
 }
 

@@ -345,14 +345,27 @@ __global__ void __launch_bounds__(KC_THREADS) preprocess_backward_compact_kernel
         const size_t si = (size_t)(valid ? i : 0);
         // stage the warp's SH coefficient rows (only needed for the view-direction term, degree >= 1)
         if (a.D > 0) {
-            for (int r = 0; r < 32; r++) {
-                const int ir = __shfl_sync(FULL, i, r);
-                if (ir < 0) continue;
-                const float* src = a.rest + (size_t)ir * a.rest_stride;
-                float* dst = rows + r * KC_ROW;
-                if (lane < 3) dst[lane] = __ldg(a.dc + (size_t)ir * 3 + lane);
-                if (lane < nrest_act) dst[3 + lane] = __ldg(src + lane);
-                if (lane + 32 < nrest_act) dst[3 + 32 + lane] = __ldg(src + 32 + lane);
+#pragma unroll 1
+            for (int r0 = 0; r0 < 32; r0 += 8) {   // eight rows' loads in flight, then their shared-memory stores
+                float v0[8], v1[8], v2[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int ir = __shfl_sync(FULL, i, r0 + u);
+                    v0[u] = v1[u] = v2[u] = 0.f;
+                    if (ir >= 0) {
+                        const float* src = a.rest + (size_t)ir * a.rest_stride;
+                        if (lane < 3) v0[u] = __ldg(a.dc + (size_t)ir * 3 + lane);
+                        if (lane < nrest_act) v1[u] = __ldg(src + lane);
+                        if (lane + 32 < nrest_act) v2[u] = __ldg(src + 32 + lane);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    float* dst = rows + (r0 + u) * KC_ROW;
+                    if (lane < 3) dst[lane] = v0[u];
+                    if (lane < nrest_act) dst[3 + lane] = v1[u];
+                    if (lane + 32 < nrest_act) dst[3 + 32 + lane] = v2[u];
+                }
             }
             __syncwarp();
         }

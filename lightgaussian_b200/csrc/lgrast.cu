@@ -1248,25 +1248,23 @@ int forward_impl(const lgr_view* v, int P, int M, const float* means3D, const fl
             sa.header = geo.num_rendered; sa.ranges = nullptr; sa.capacity = 0;
             // 11 + 11 + 10 bits: depth_keys -> (depth_keys_sorted, sorted_ids) -> (depth_keys, iota) -> sorted_ids
             dsort_count_kernel<0, true><<<BIN_V, 256, 0, stream>>>(geo.depth_keys, P, per_block, img.bin_M, geo.num_rendered);
-            bin_scan_kernel<false><<<DS_BINS / 32, 256, 0, stream>>>(sa);
+            bin_scan_kernel<false><<<DS_BINS / 32, SCAN_THREADS, 0, stream>>>(sa);
             dsort_scatter_kernel<0, true, false><<<BIN_V, 256, 0, stream>>>(geo.depth_keys, nullptr, geo.depth_keys_sorted, geo.sorted_ids, img.bin_M,
                                                                            img.bin_base, P, per_block);
             dsort_count_kernel<DS_BITS, false><<<BIN_V, 256, 0, stream>>>(geo.depth_keys_sorted, P, per_block, img.bin_M, geo.num_rendered);
-            bin_scan_kernel<false><<<DS_BINS / 32, 256, 0, stream>>>(sa);
+            bin_scan_kernel<false><<<DS_BINS / 32, SCAN_THREADS, 0, stream>>>(sa);
             dsort_scatter_kernel<DS_BITS, false, false><<<BIN_V, 256, 0, stream>>>(geo.depth_keys_sorted, geo.sorted_ids, geo.depth_keys, geo.iota,
                                                                                   img.bin_M, img.bin_base, P, per_block);
             dsort_count_kernel<2 * DS_BITS, false><<<BIN_V, 256, 0, stream>>>(geo.depth_keys, P, per_block, img.bin_M, geo.num_rendered);
-            bin_scan_kernel<false><<<DS_BINS / 32, 256, 0, stream>>>(sa);
+            bin_scan_kernel<false><<<DS_BINS / 32, SCAN_THREADS, 0, stream>>>(sa);
             dsort_scatter_kernel<2 * DS_BITS, false, true><<<BIN_V, 256, 0, stream>>>(geo.depth_keys, geo.iota, nullptr, geo.sorted_ids, img.bin_M,
                                                                                       img.bin_base, P, per_block);
             g_launches.fetch_add(8, std::memory_order_relaxed);
             LGR_LAUNCH_CHECK("depth sort kernels", debug, stream);
         }
-        const size_t tb_smem = sizeof(uint32_t) * (size_t)tiles_pad;
-        if (tb_smem > 48 * 1024) {
-            LGR_CUDA_TRY(cudaFuncSetAttribute(tile_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tb_smem));
-            LGR_CUDA_TRY(cudaFuncSetAttribute(tile_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tb_smem));
-        }
+        const size_t tb_smem = sizeof(uint32_t) * (size_t)tiles_pad, ts_smem = tile_scatter_smem(tiles_pad);
+        if (tb_smem > 48 * 1024) LGR_CUDA_TRY(cudaFuncSetAttribute(tile_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tb_smem));
+        if (ts_smem > 48 * 1024) LGR_CUDA_TRY(cudaFuncSetAttribute(tile_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ts_smem));
         const bool exact = g_bin_mode == 1;
         size_t capacity = 0;
         if (!exact) {   // size the blob now, from the running estimate
@@ -1283,14 +1281,14 @@ int forward_impl(const lgr_view* v, int P, int M, const float* means3D, const fl
             sa.M = img.bin_M; sa.V = BIN_V; sa.bins = tiles; sa.bins_pad = tiles_pad; sa.bin_total = img.bin_total; sa.bin_base = img.bin_base;
             sa.header = geo.num_rendered; sa.ranges = img.ranges;
             sa.capacity = exact ? 0xffffffffu : (uint32_t)std::min(capacity, (size_t)0x7fffffff);
-            bin_scan_kernel<true><<<tiles_pad / 32, 256, 0, stream>>>(sa);
+            bin_scan_kernel<true><<<tiles_pad / 32, SCAN_THREADS, 0, stream>>>(sa);
             g_launches.fetch_add(1, std::memory_order_relaxed);
             LGR_LAUNCH_CHECK("tile_count_kernel", debug, stream);
         }
         LGR_CUDA_TRY(cudaMemcpyAsync(host_hdr, geo.num_rendered, 4 * sizeof(int), cudaMemcpyDeviceToHost, stream));
         auto launch_scatter = [&]() -> int {
             ProfScope ps(ST_BIN_SCATTER, stream);
-            tile_scatter_kernel<<<BIN_V, TB_THREADS, tb_smem, stream>>>(geo.sorted_ids, geo.bin_rec, P, per_block, gx, tiles_pad, img.bin_M, img.bin_base,
+            tile_scatter_kernel<<<BIN_V, TB_THREADS, ts_smem, stream>>>(geo.sorted_ids, geo.bin_rec, P, per_block, gx, tiles_pad, img.bin_M, img.bin_base,
                                                                         geo.num_rendered, bin.point_list);
             LGR_LAUNCH_CHECK("tile_scatter_kernel", debug, stream);
             return LGR_OK;
