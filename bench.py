@@ -637,8 +637,10 @@ def main():
             "depth_sort(dsort_count+bin_scan+dsort_scatter x3)": 16 * P, "tile_count_kernel+bin_scan_kernel": 20 * P,
             "tile_scatter_kernel": 20 * P + 4 * R,
             "blend_forward_kernel": 40 * R + 20 * N,
-            "blend_backward_kernel": 20 * N + 40 * R + 44 * Pv,
-            "preprocess_backward_kernel": 44 * Pv + 12 * P + Pv * (32 + 12 * M) + P * (56 + 12 * M),
+            # the P*(56+12M) bytes of dense gradient rows are written (cleared) by the blend backward's producer thread in kback mode 0,
+            # by the K7+K8 kernels otherwise: the bytes follow the kernel that moves them
+            "blend_backward_kernel": 20 * N + 40 * R + 44 * Pv + (P * (56 + 12 * M) if args.kback_mode == 0 else 0),
+            "preprocess_backward_kernel": 44 * Pv + 12 * P + Pv * (32 + 12 * M) + (0 if args.kback_mode == 0 else P * (56 + 12 * M)),
             "memset": 48 * P,
             "sh_grad_from_views_kernel": 12 * P + 12 * P * world + 12 * M * P,
             "peer_allreduce_kernel": 2 * 44 * P * (world - 1) / max(world, 1),
@@ -656,7 +658,7 @@ def main():
         if os.path.exists(tpath) and (P, W, H) == (3_000_000, 1920, 1080):
             for kname, bytes_ in json.load(open(tpath))["dram_bytes_per_launch"].items():
                 if kname.split("<")[0].replace("_raw", "") == top.replace("_raw", ""):
-                    traffic = bytes_
+                    traffic = bytes_      # ncu capture named in profiles/ncu_traffic.json["source"] (scripts/ncu_traffic.py)
         roofline = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                     "traffic": traffic, "peak_source": peak_src,
                     "share_of_native_time": stages[top]["ms_per_launch"] * stages[top]["launches"] / nprof / tot_ms,

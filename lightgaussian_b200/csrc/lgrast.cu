@@ -1263,8 +1263,9 @@ int forward_impl(const lgr_view* v, int P, int M, const float* means3D, const fl
             LGR_LAUNCH_CHECK("depth sort kernels", debug, stream);
         }
         const size_t tb_smem = sizeof(uint32_t) * (size_t)tiles_pad, ts_smem = tile_scatter_smem(tiles_pad);
-        if (tb_smem > 48 * 1024) LGR_CUDA_TRY(cudaFuncSetAttribute(tile_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tb_smem));
-        if (ts_smem > 48 * 1024) LGR_CUDA_TRY(cudaFuncSetAttribute(tile_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ts_smem));
+        // always: static + dynamic shared memory together may pass 48 KB even when the dynamic part alone does not
+        LGR_CUDA_TRY(cudaFuncSetAttribute(tile_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(tb_smem, (size_t)48 * 1024)));
+        LGR_CUDA_TRY(cudaFuncSetAttribute(tile_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(ts_smem, (size_t)48 * 1024)));
         const bool exact = g_bin_mode == 1;
         size_t capacity = 0;
         if (!exact) {   // size the blob now, from the running estimate
