@@ -65,6 +65,31 @@ __device__ __forceinline__ unsigned warp_match(uint32_t key, bool valid)
     return valid ? m : 0u;
 }
 
+// shared-memory mbarriers (the tile scatter's turn hand-off): a waiting warp is suspended by the hardware instead of polling
+__device__ __forceinline__ uint32_t bin_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bin_mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bin_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bin_mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bin_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bin_mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    uint32_t ok = 0;
+    for (uint32_t spin = 0; !ok; ++spin) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok)
+                     : "r"(bin_smem_u32(bar)), "r"(parity)
+                     : "memory");
+        if (!ok && spin > (1u << 26)) {   // a protocol bug becomes an error, not a hung GPU
+            printf("lgrast: tile scatter turn barrier timed out (block %d warp %d)\n", (int)blockIdx.x, (int)(threadIdx.x >> 5));
+            __trap();
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // depth sort: one LSD pass = count -> scan -> scatter
 // ------------------------------------------------------------------------------------------------
@@ -134,71 +159,99 @@ __global__ void __launch_bounds__(SCAN_THREADS) bin_scan_kernel(BinScanArgs a)
     }
     if (warp == 0) a.bin_total[bin] = total;
 
-    // the last block to arrive scans the bin totals
+    // the last block to arrive scans the bin totals: every warp takes a contiguous segment, lanes read it 32 bins at a time (all the
+    // segment's loads in flight before the carry chain starts), a warp scan per 32 bins, then the warp offsets
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) last = atomicAdd(reinterpret_cast<unsigned*>(a.header + HDR_DONE), 1u) == gridDim.x - 1;
     __syncthreads();
     if (!last) return;
     __threadfence();
-    const int chunk = a.bins_pad / 256;   // consecutive bins per thread (threads 0..255)
-    const int c0 = threadIdx.x * chunk;
+    constexpr int TB = 16;                                  // 32-bin groups fetched at once
+    const int seg = a.bins_pad / NW;                          // bins per warp (bins_pad is a multiple of 256 = 16 warps x 16)
+    const int nit = (seg + 31) / 32;
+    const int sbase = warp * seg;
     uint32_t mine = 0;
-    if (threadIdx.x < 256)
-        for (int i = 0; i < chunk; i++) mine += __ldcg(a.bin_total + c0 + i);
-    uint32_t incl = mine;
+    for (int it0 = 0; it0 < nit; it0 += TB) {
+        uint32_t c[TB];
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t t = __shfl_up_sync(FULL, incl, d);
-        if (lane >= d) incl += t;
+        for (int u = 0; u < TB; u++) {
+            const int o = (it0 + u) * 32 + lane;
+            c[u] = (it0 + u < nit && o < seg) ? __ldcg(a.bin_total + sbase + o) : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < TB; u++) mine += c[u];
     }
-    if (lane == 31) wsum[warp] = incl;
+    mine = __reduce_add_sync(FULL, mine);
+    if (lane == 0) wsum[warp] = mine;
     __syncthreads();
-    if (threadIdx.x >= 256) return;
-    uint32_t base = incl - mine;
-    for (int w = 0; w < warp; w++) base += wsum[w];
-    for (int i = 0; i < chunk; i++) {
-        const uint32_t c = __ldcg(a.bin_total + c0 + i);
-        a.bin_base[c0 + i] = base;
-        if (TILES && c0 + i < a.bins) a.ranges[c0 + i] = c ? make_uint2(base, base + c) : make_uint2(0u, 0u);   // empty tiles: (0,0), the reference's memset
-        base += c;
+    uint32_t carry = 0, grand = 0;
+#pragma unroll
+    for (int w = 0; w < NW; w++) {
+        const uint32_t t = wsum[w];
+        if (w < warp) carry += t;
+        grand += t;
     }
-    if (threadIdx.x == 255) {
+    for (int it0 = 0; it0 < nit; it0 += TB) {
+        uint32_t c[TB];
+#pragma unroll
+        for (int u = 0; u < TB; u++) {
+            const int o = (it0 + u) * 32 + lane;
+            c[u] = (it0 + u < nit && o < seg) ? __ldcg(a.bin_total + sbase + o) : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < TB; u++) {
+            uint32_t incl = c[u];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t t = __shfl_up_sync(FULL, incl, d);
+                if (lane >= d) incl += t;
+            }
+            const int o = (it0 + u) * 32 + lane;
+            if (it0 + u < nit && o < seg) {
+                const uint32_t bs = carry + incl - c[u];
+                a.bin_base[sbase + o] = bs;
+                if (TILES && sbase + o < a.bins) a.ranges[sbase + o] = c[u] ? make_uint2(bs, bs + c[u]) : make_uint2(0u, 0u);   // empty tiles: (0,0), the reference's memset
+            }
+            carry += __shfl_sync(FULL, incl, 31);
+        }
+    }
+    if (threadIdx.x == 0) {
         if (TILES) {
-            a.header[HDR_LISTED] = (int)base;
+            a.header[HDR_LISTED] = (int)grand;
             a.header[HDR_CAPACITY] = (int)a.capacity;
-            a.header[HDR_OVERFLOW] = base > a.capacity ? 1 : 0;
+            a.header[HDR_OVERFLOW] = grand > a.capacity ? 1 : 0;
         }
         a.header[HDR_DONE] = 0;   // ready for the next pass
     }
 }
 
-// Scatter of one depth-sort pass.  The block's chunk is cut into 8 contiguous sub-chunks, one per warp, so that "input order" inside the
+// Scatter of one depth-sort pass.  The block's chunk is cut into 4 contiguous sub-chunks, one per warp, so that "input order" inside the
 // block is (warp, position in the warp's sub-chunk) and no warp ever waits for another: pass A counts every warp's digits into ITS row of
-// a shared 8 x 2048 table of 16-bit counters, a prefix over the 8 rows turns the counts into each warp's first slot per digit, pass B
-// walks the sub-chunk again and hands out the slots in order.  Keys are fetched four steps ahead (and come from L1 in pass B).
-// per_block <= 65 535 keeps the counters in 16 bits.
+// a shared 4 x 2048 table (shared-memory atomics, no ordering needed), a prefix over the 4 rows turns the counts into each warp's first
+// slot per digit, pass B walks the sub-chunk again and hands out the slots in order (warp_match + one read-modify-write per group).
+// Keys are fetched four steps ahead (and come from L1 in pass B).
 constexpr int DS_AHEAD = 4;
+constexpr int DS_THREADS = 128;
 
 template <int SHIFT, bool FIRST, bool LAST>
-__global__ void __launch_bounds__(256) dsort_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ ids_in,
-                                                            uint32_t* __restrict__ keys_out, uint32_t* __restrict__ ids_out,
-                                                            const uint32_t* __restrict__ E, const uint32_t* __restrict__ bin_base, int P, int per_block)
+__global__ void __launch_bounds__(DS_THREADS) dsort_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ ids_in,
+                                                                   uint32_t* __restrict__ keys_out, uint32_t* __restrict__ ids_out,
+                                                                   const uint32_t* __restrict__ E, const uint32_t* __restrict__ bin_base, int P,
+                                                                   int per_block)
 {
     constexpr int BITS = (32 - SHIFT) < DS_BITS ? (32 - SHIFT) : DS_BITS;
-    __shared__ uint16_t wcnt[8][DS_BINS];
+    constexpr int NW = DS_THREADS / 32;
+    __shared__ uint32_t wcnt[NW][DS_BINS];
     __shared__ uint32_t base[DS_BINS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    {
-        uint32_t* z = reinterpret_cast<uint32_t*>(&wcnt[0][0]);
-        for (int i = threadIdx.x; i < 8 * DS_BINS / 2; i += 256) z[i] = 0u;
-        for (int i = threadIdx.x; i < DS_BINS; i += 256) base[i] = bin_base[i] + E[(size_t)blockIdx.x * DS_BINS + i];
-    }
+    for (int i = threadIdx.x; i < NW * DS_BINS; i += DS_THREADS) (&wcnt[0][0])[i] = 0u;
+    for (int i = threadIdx.x; i < DS_BINS; i += DS_THREADS) base[i] = bin_base[i] + E[(size_t)blockIdx.x * DS_BINS + i];
     __syncthreads();
     const int lo = blockIdx.x * per_block, hi = min(P, lo + per_block);
-    const int per_warp = per_block / 8;   // per_block is a multiple of 256
+    const int per_warp = per_block / NW;   // per_block is a multiple of 256
     const int wlo = lo + warp * per_warp, whi = min(hi, wlo + per_warp);
-    uint16_t* mine = wcnt[warp];
+    uint32_t* mine = wcnt[warp];
     for (int k0 = wlo; k0 < whi; k0 += 32 * DS_AHEAD) {
         uint32_t key[DS_AHEAD];
 #pragma unroll
@@ -207,21 +260,16 @@ __global__ void __launch_bounds__(256) dsort_scatter_kernel(const uint32_t* __re
             key[j] = k < whi ? keys_in[k] : 0u;
         }
 #pragma unroll
-        for (int j = 0; j < DS_AHEAD; j++) {
-            const bool valid = k0 + 32 * j + lane < whi;
-            const uint32_t d = (key[j] >> SHIFT) & (DS_BINS - 1);
-            const unsigned m = warp_match<BITS>(d, valid);
-            if (valid && lane == __ffs(m) - 1) mine[d] = (uint16_t)(mine[d] + __popc(m));
-            __syncwarp();
-        }
+        for (int j = 0; j < DS_AHEAD; j++)
+            if (k0 + 32 * j + lane < whi) atomicAdd(&mine[(key[j] >> SHIFT) & (DS_BINS - 1)], 1u);
     }
     __syncthreads();
-    for (int d = threadIdx.x; d < DS_BINS; d += 256) {
-        uint32_t run = 0;
+    for (int d = threadIdx.x; d < DS_BINS; d += DS_THREADS) {
+        uint32_t run = base[d];
 #pragma unroll
-        for (int w = 0; w < 8; w++) {
+        for (int w = 0; w < NW; w++) {
             const uint32_t c = wcnt[w][d];
-            wcnt[w][d] = (uint16_t)run;
+            wcnt[w][d] = run;
             run += c;
         }
     }
@@ -245,12 +293,12 @@ __global__ void __launch_bounds__(256) dsort_scatter_kernel(const uint32_t* __re
             uint32_t old = 0;
             if (valid && lane == leader) {
                 old = mine[d];
-                mine[d] = (uint16_t)(old + __popc(m));
+                mine[d] = old + (uint32_t)__popc(m);
             }
             __syncwarp();
             old = __shfl_sync(FULL, old, leader & 31);
             if (valid) {
-                const uint32_t pos = base[d] + old + (uint32_t)__popc(m & lt);
+                const uint32_t pos = old + (uint32_t)__popc(m & lt);
                 if (!LAST) keys_out[pos] = key[j];
                 ids_out[pos] = id[j];
             }
@@ -341,6 +389,23 @@ __device__ __forceinline__ uint32_t bin_row_instance(const BinRow& r, uint32_t j
     return (uint32_t)((o_y0 + ry) * gx + (o_x0 + rx));
 }
 
+// the lane's OWN Gaussian (rectangle of at most 64 tiles): its kept tiles in row-major order -> f(tile, j), j = 0 .. cnt-1.
+// For rows of small splats (the common case: 3-4 kept tiles per Gaussian) this per-lane walk costs a third of the instructions of the
+// warp-cooperative expansion (owner search + seven shuffles per instance), which remains the path for rows with larger rectangles.
+template <class F>
+__device__ __forceinline__ void bin_lane_tiles(const BinRow& r, int gx, F f)
+{
+    unsigned long long m = r.cnt ? r.mask : 0ull;
+    const float fw = (float)r.w;
+    uint32_t j = 0;
+    while (m) {
+        const int b = __ffsll((long long)m) - 1;
+        m &= m - 1;
+        const int ry = (int)__fdividef((float)b + 0.5f, fw), rx = b - ry * r.w;
+        f((uint32_t)((r.y0 + ry) * gx + (r.x0 + rx)), j++);
+    }
+}
+
 __global__ void __launch_bounds__(TC_THREADS) tile_count_kernel(const uint32_t* __restrict__ sorted_ids, const uint4* __restrict__ bin_rec, int P,
                                                                 int per_block, int gx, int tiles_pad, uint32_t* __restrict__ M, int* __restrict__ header)
 {
@@ -360,11 +425,15 @@ __global__ void __launch_bounds__(TC_THREADS) tile_count_kernel(const uint32_t* 
         BinRow r;
         bin_row_decode(cur, lane, r);
         area += r.area;
-        for (uint32_t base = 0; base < r.total; base += 32) {
-            uint32_t owner;
-            int olane;
-            const uint32_t tile = bin_row_instance(r, base + lane, gx, owner, olane);
-            if (tile != BIN_NONE) atomicAdd(&hist[tile], 1u);
+        if (__all_sync(FULL, r.area <= 64u)) {
+            bin_lane_tiles(r, gx, [&](uint32_t tile, uint32_t) { atomicAdd(&hist[tile], 1u); });
+        } else {
+            for (uint32_t base = 0; base < r.total; base += 32) {
+                uint32_t owner;
+                int olane;
+                const uint32_t tile = bin_row_instance(r, base + lane, gx, owner, olane);
+                if (tile != BIN_NONE) atomicAdd(&hist[tile], 1u);
+            }
         }
     }
     __syncthreads();
@@ -381,44 +450,58 @@ __global__ void __launch_bounds__(TB_THREADS) tile_scatter_kernel(const uint32_t
                                                                   const uint32_t* __restrict__ bin_base, const int* __restrict__ header,
                                                                   uint32_t* __restrict__ point_list)
 {
-    // Ahead of its turn a warp loads its row (the next row's loads are already in flight), generates the row's instances and groups the
-    // 32 instances of every step by tile (warp_match); per instance it parks {tile | owner lane << 16, group mask} in its shared buffer.
-    // Inside the turn a step is: one 64-bit shared load, the group's lowest lane reads and bumps the tile's cursor, one shuffle.
+    // Ahead of its turn a warp loads its row (the next row's loads are already in flight), writes the row's instances in row order
+    // (Gaussian after Gaussian, tiles row-major) as {tile | owner lane << 16, group mask} into its shared buffer -- the group mask of an
+    // instance = the lanes of its 32-instance step that hold the same tile (warp_match).  Inside the turn a step is: one 64-bit shared
+    // load, the group's lowest lane reads and bumps the tile's cursor, one shuffle, one store.  Turns are handed on through one
+    // mbarrier per warp (arrive on the next warp's barrier), so waiting warps are suspended, not polling shared memory.
     extern __shared__ uint32_t tb_smem[];
     uint32_t* cursor = tb_smem;                                      // [tiles_pad]
     uint2* gen = reinterpret_cast<uint2*>(tb_smem + tiles_pad);      // [warps][TB_BUF]
-    __shared__ int turn;
+    constexpr int NW = TB_THREADS / 32;
+    __shared__ __align__(8) uint64_t tbar[NW];
     for (int i = threadIdx.x; i < tiles_pad; i += TB_THREADS) cursor[i] = bin_base[i] + E[(size_t)blockIdx.x * tiles_pad + i];
-    if (threadIdx.x == 0) turn = 0;
+    if (threadIdx.x == 0) {
+        for (int w = 0; w < NW; w++) bin_mbar_init(&tbar[w], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        bin_mbar_arrive(&tbar[0]);   // turn 0 belongs to warp 0
+    }
     __syncthreads();
     const uint32_t capacity = (uint32_t)header[HDR_CAPACITY];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int lo = blockIdx.x * per_block, hi = min(P, lo + per_block);
     const int nrows = (hi - lo + 31) / 32;
     const unsigned lt = (1u << lane) - 1u;
-    constexpr int NW = TB_THREADS / 32;
     uint2* buf = gen + warp * TB_BUF;
-    volatile int* vturn = &turn;
     BinRowRaw next = bin_row_fetch(sorted_ids, bin_rec, lo + warp * 32 + lane, hi);
-    for (int t = warp; t < nrows; t += NW) {
+    uint32_t phase = 0;
+    for (int t = warp; t < nrows; t += NW, phase ^= 1u) {
         const BinRowRaw cur = next;
         next = bin_row_fetch(sorted_ids, bin_rec, lo + (t + NW) * 32 + lane, hi);
         BinRow r;
         bin_row_decode(cur, lane, r);
         const bool staged = r.total <= (uint32_t)TB_BUF;
         if (staged) {
+            if (__all_sync(FULL, r.area <= 64u)) {
+                bin_lane_tiles(r, gx, [&](uint32_t tile, uint32_t j) { buf[r.off + j].x = tile | ((uint32_t)lane << 16); });
+            } else {
+                for (uint32_t base = 0; base < r.total; base += 32) {
+                    uint32_t owner;
+                    int olane;
+                    const uint32_t tile = bin_row_instance(r, base + lane, gx, owner, olane);
+                    if (tile != BIN_NONE) buf[base + lane].x = tile | ((uint32_t)olane << 16);
+                }
+            }
+            __syncwarp();
             for (uint32_t base = 0; base < r.total; base += 32) {
-                uint32_t owner;
-                int olane;
-                const uint32_t tile = bin_row_instance(r, base + lane, gx, owner, olane);
-                const unsigned m = warp_match<16>(tile, tile != BIN_NONE);
-                if (tile != BIN_NONE) buf[base + lane] = make_uint2(tile | ((uint32_t)olane << 16), m);
+                const bool valid = base + lane < r.total;
+                const uint32_t tile = valid ? (buf[base + lane].x & 0xffffu) : 0u;
+                const unsigned m = warp_match<16>(tile, valid);
+                if (valid) buf[base + lane].y = m;
             }
             __syncwarp();
         }
-        if (lane == 0)
-            while (*vturn != t) {}
-        __syncwarp();
+        bin_mbar_wait(&tbar[warp], phase);
         for (uint32_t base = 0; base < r.total; base += 32) {
             uint32_t tile = BIN_NONE, owner = 0;
             unsigned m = 0;
@@ -447,7 +530,7 @@ __global__ void __launch_bounds__(TB_THREADS) tile_scatter_kernel(const uint32_t
             if (tile != BIN_NONE && pos < capacity) point_list[pos] = owner;
         }
         __syncwarp();
-        if (lane == 0) *vturn = t + 1;
+        if (lane == 0) bin_mbar_arrive(&tbar[(warp + 1) % NW]);   // release: the next row's warp may go
     }
 }
 

@@ -1249,15 +1249,15 @@ int forward_impl(const lgr_view* v, int P, int M, const float* means3D, const fl
             // 11 + 11 + 10 bits: depth_keys -> (depth_keys_sorted, sorted_ids) -> (depth_keys, iota) -> sorted_ids
             dsort_count_kernel<0, true><<<BIN_V, 256, 0, stream>>>(geo.depth_keys, P, per_block, img.bin_M, geo.num_rendered);
             bin_scan_kernel<false><<<DS_BINS / 32, SCAN_THREADS, 0, stream>>>(sa);
-            dsort_scatter_kernel<0, true, false><<<BIN_V, 256, 0, stream>>>(geo.depth_keys, nullptr, geo.depth_keys_sorted, geo.sorted_ids, img.bin_M,
+            dsort_scatter_kernel<0, true, false><<<BIN_V, DS_THREADS, 0, stream>>>(geo.depth_keys, nullptr, geo.depth_keys_sorted, geo.sorted_ids, img.bin_M,
                                                                            img.bin_base, P, per_block);
             dsort_count_kernel<DS_BITS, false><<<BIN_V, 256, 0, stream>>>(geo.depth_keys_sorted, P, per_block, img.bin_M, geo.num_rendered);
             bin_scan_kernel<false><<<DS_BINS / 32, SCAN_THREADS, 0, stream>>>(sa);
-            dsort_scatter_kernel<DS_BITS, false, false><<<BIN_V, 256, 0, stream>>>(geo.depth_keys_sorted, geo.sorted_ids, geo.depth_keys, geo.iota,
+            dsort_scatter_kernel<DS_BITS, false, false><<<BIN_V, DS_THREADS, 0, stream>>>(geo.depth_keys_sorted, geo.sorted_ids, geo.depth_keys, geo.iota,
                                                                                   img.bin_M, img.bin_base, P, per_block);
             dsort_count_kernel<2 * DS_BITS, false><<<BIN_V, 256, 0, stream>>>(geo.depth_keys, P, per_block, img.bin_M, geo.num_rendered);
             bin_scan_kernel<false><<<DS_BINS / 32, SCAN_THREADS, 0, stream>>>(sa);
-            dsort_scatter_kernel<2 * DS_BITS, false, true><<<BIN_V, 256, 0, stream>>>(geo.depth_keys, geo.iota, nullptr, geo.sorted_ids, img.bin_M,
+            dsort_scatter_kernel<2 * DS_BITS, false, true><<<BIN_V, DS_THREADS, 0, stream>>>(geo.depth_keys, geo.iota, nullptr, geo.sorted_ids, img.bin_M,
                                                                                       img.bin_base, P, per_block);
             g_launches.fetch_add(8, std::memory_order_relaxed);
             LGR_LAUNCH_CHECK("depth sort kernels", debug, stream);
