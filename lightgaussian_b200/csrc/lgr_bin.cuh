@@ -19,10 +19,9 @@
 //               (warp_match: cost = number of bits, where __match_any_sync costs one round per DISTINCT value -- measured 10x
 //               slower on these mostly-distinct keys), the lowest lane of each group bumps a shared-memory counter, the others
 //               add their position in the group.  Depth sort (2048 bins): every warp owns a contiguous eighth of the chunk and
-//               a private row of 16-bit counters, no warp waits for another.  Tile pass (8160 bins, one 32-bit cursor per tile):
-//               the cursor updates of a block must follow the depth order, so warps take turns row by row (a shared ticket);
-//               loads, instance generation and the group masks are computed before the turn, inside it a step is one shared load,
-//               one cursor read-modify-write and a shuffle.
+//               a private row of counters, no warp waits for another.  Tile pass (8160 bins, one 32-bit cursor per tile): the
+//               cursor updates of a block must follow the depth order; one ranking warp owns the cursors and consumes rows that
+//               seven producer warps prepare ahead of it through a ring of shared-memory slots (full / empty mbarriers).
 //
 // The instance count R is needed on the host only to size the binning blob.  The blob is sized from a running estimate BEFORE the
 // count is known; the kernels bound every store by that capacity and raise a flag when it is too small, the host looks at the
@@ -38,7 +37,7 @@ constexpr int DS_BINS = 1 << DS_BITS;
 constexpr uint32_t BIN_NONE = 0xffffffffu;
 constexpr int TB_THREADS = 256;       // tile scatter block: 8 warps
 constexpr int TC_THREADS = 256;       // tile count block: 8 warps
-constexpr int TB_BUF = 256;           // instances of one 32-Gaussian row a scatter warp prepares ahead of its turn
+constexpr int TB_BUF = 256;           // instances of one 32-Gaussian row that fit a ring slot of the tile scatter
 constexpr int SCAN_THREADS = 512;     // scan block: 16 warps share the rows of a 32-bin strip
 constexpr int SCAN_ROWS = 40;         // rows per scan warp held in registers: BIN_V <= 16 * 40
 constexpr int BIN_MAX_TILES = 32768;  // shared-memory cursor per tile (4 B) + staging: above this the library path is used
@@ -445,28 +444,45 @@ __global__ void __launch_bounds__(TC_THREADS) tile_count_kernel(const uint32_t* 
     if (lane == 0 && area) atomicAdd(reinterpret_cast<unsigned*>(header + HDR_RENDERED), area);
 }
 
-inline size_t tile_scatter_smem(int tiles_pad) { return sizeof(uint32_t) * (size_t)tiles_pad + sizeof(uint2) * (size_t)(TB_THREADS / 32) * TB_BUF; }
+// ---- tile scatter: seven producer warps, one ranking warp, a ring of row slots between them ----
+constexpr int TS_SLOTS = 8;                 // rows in flight between producers and the ranker
+constexpr int TS_SLOT = TB_BUF;             // instances a slot holds (one 32-Gaussian row; larger rows travel raw)
+constexpr int TS_PRODUCERS = TB_THREADS / 32 - 1;
+constexpr uint32_t TS_RAW = 0xffffffffu;
+
+struct TileSlot {
+    uint32_t mask[TS_SLOT];   // group mask of the instance inside its 32-instance step   (raw rows: the 32 bin records, 4 words each)
+    uint32_t id[TS_SLOT];     // Gaussian id                                              (raw rows: the 32 ids)
+    uint16_t tile[TS_SLOT];
+};
+
+inline size_t tile_scatter_smem(int tiles_pad) { return sizeof(uint32_t) * (size_t)tiles_pad + sizeof(TileSlot) * TS_SLOTS; }
 
 __global__ void __launch_bounds__(TB_THREADS) tile_scatter_kernel(const uint32_t* __restrict__ sorted_ids, const uint4* __restrict__ bin_rec, int P,
                                                                   int per_block, int gx, int tiles_pad, const uint32_t* __restrict__ E,
                                                                   const uint32_t* __restrict__ bin_base, const int* __restrict__ header,
                                                                   uint32_t* __restrict__ point_list)
 {
-    // Ahead of its turn a warp loads its row (the next row's loads are already in flight), writes the row's instances in row order
-    // (Gaussian after Gaussian, tiles row-major) as {tile | owner lane << 16, group mask} into its shared buffer -- the group mask of an
-    // instance = the lanes of its 32-instance step that hold the same tile (warp_match).  Inside the turn a step is: one 64-bit shared
-    // load, the group's lowest lane reads and bumps the tile's cursor, one shuffle, one store.  Turns are handed on through one
-    // mbarrier per warp (arrive on the next warp's barrier), so waiting warps are suspended, not polling shared memory.
+    // The cursor of a tile must be advanced in depth order, i.e. row after row of the block's chunk.  ONE warp (the ranker) owns the
+    // cursors and walks the rows in order; the other seven warps prepare rows ahead of it: load (the next row's loads already in flight),
+    // expand the row into its instances in row order, group every 32-instance step by tile (warp_match), and publish {tile, group mask,
+    // Gaussian id} per instance in a ring slot (full / empty mbarriers, as in the blend kernels).  Per step the ranker does three shared
+    // loads, one cursor read-modify-write by the lowest lane of each group, one shuffle and the store -- nothing else sits on the serial
+    // path, and nobody but the ranker ever waits on the critical hand-off.  (Earlier versions passed a ticket between eight equal warps:
+    // the seven waiting warps' polling -- shared-memory spin, __nanosleep or mbarrier.try_wait alike -- slowed the one working warp 5-10x.)
     extern __shared__ uint32_t tb_smem[];
-    uint32_t* cursor = tb_smem;                                      // [tiles_pad]
-    uint2* gen = reinterpret_cast<uint2*>(tb_smem + tiles_pad);      // [warps][TB_BUF]
-    constexpr int NW = TB_THREADS / 32;
-    __shared__ __align__(8) uint64_t tbar[NW];
+    uint32_t* cursor = tb_smem;                                              // [tiles_pad]
+    TileSlot* slots = reinterpret_cast<TileSlot*>(tb_smem + tiles_pad);      // [TS_SLOTS]
+    __shared__ __align__(8) uint64_t full[TS_SLOTS];
+    __shared__ __align__(8) uint64_t empty[TS_SLOTS];
+    __shared__ uint32_t slot_n[TS_SLOTS];
     for (int i = threadIdx.x; i < tiles_pad; i += TB_THREADS) cursor[i] = bin_base[i] + E[(size_t)blockIdx.x * tiles_pad + i];
     if (threadIdx.x == 0) {
-        for (int w = 0; w < NW; w++) bin_mbar_init(&tbar[w], 1);
+        for (int k = 0; k < TS_SLOTS; k++) {
+            bin_mbar_init(&full[k], 1);
+            bin_mbar_init(&empty[k], 1);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        bin_mbar_arrive(&tbar[0]);   // turn 0 belongs to warp 0
     }
     __syncthreads();
     const uint32_t capacity = (uint32_t)header[HDR_CAPACITY];
@@ -474,65 +490,106 @@ __global__ void __launch_bounds__(TB_THREADS) tile_scatter_kernel(const uint32_t
     const int lo = blockIdx.x * per_block, hi = min(P, lo + per_block);
     const int nrows = (hi - lo + 31) / 32;
     const unsigned lt = (1u << lane) - 1u;
-    uint2* buf = gen + warp * TB_BUF;
-    BinRowRaw next = bin_row_fetch(sorted_ids, bin_rec, lo + warp * 32 + lane, hi);
-    uint32_t phase = 0;
-    for (int t = warp; t < nrows; t += NW, phase ^= 1u) {
-        const BinRowRaw cur = next;
-        next = bin_row_fetch(sorted_ids, bin_rec, lo + (t + NW) * 32 + lane, hi);
-        BinRow r;
-        bin_row_decode(cur, lane, r);
-        const bool staged = r.total <= (uint32_t)TB_BUF;
-        if (staged) {
-            if (__all_sync(FULL, r.area <= 64u)) {
-                bin_lane_tiles(r, gx, [&](uint32_t tile, uint32_t j) { buf[r.off + j].x = tile | ((uint32_t)lane << 16); });
-            } else {
+
+    if (warp < TS_PRODUCERS) {
+        BinRowRaw next = bin_row_fetch(sorted_ids, bin_rec, lo + warp * 32 + lane, hi);
+        for (int t = warp; t < nrows; t += TS_PRODUCERS) {
+            const BinRowRaw cur = next;
+            next = bin_row_fetch(sorted_ids, bin_rec, lo + (t + TS_PRODUCERS) * 32 + lane, hi);
+            BinRow r;
+            bin_row_decode(cur, lane, r);
+            const int k = t % TS_SLOTS;
+            const uint32_t ph = (uint32_t)(t / TS_SLOTS) & 1u;
+            bin_mbar_wait(&empty[k], ph ^ 1u);   // passes at once the first time round
+            TileSlot& sl = slots[k];
+            if (r.total <= (uint32_t)TS_SLOT) {
+                if (__all_sync(FULL, r.area <= 64u)) {
+                    bin_lane_tiles(r, gx, [&](uint32_t tile, uint32_t j) {
+                        sl.tile[r.off + j] = (uint16_t)tile;
+                        sl.id[r.off + j] = r.id;
+                    });
+                } else {
+                    for (uint32_t base = 0; base < r.total; base += 32) {
+                        uint32_t owner;
+                        int olane;
+                        const uint32_t tile = bin_row_instance(r, base + lane, gx, owner, olane);
+                        if (tile != BIN_NONE) {
+                            sl.tile[base + lane] = (uint16_t)tile;
+                            sl.id[base + lane] = owner;
+                        }
+                    }
+                }
+                __syncwarp();
                 for (uint32_t base = 0; base < r.total; base += 32) {
-                    uint32_t owner;
-                    int olane;
-                    const uint32_t tile = bin_row_instance(r, base + lane, gx, owner, olane);
-                    if (tile != BIN_NONE) buf[base + lane].x = tile | ((uint32_t)olane << 16);
+                    const bool valid = base + lane < r.total;
+                    const uint32_t tile = valid ? (uint32_t)sl.tile[base + lane] : 0u;
+                    const unsigned m = warp_match<16>(tile, valid);
+                    if (valid) sl.mask[base + lane] = m;
                 }
+                if (lane == 0) slot_n[k] = r.total;
+            } else {   // a row of screen-filling splats: hand the row itself to the ranker
+                sl.id[lane] = cur.id;
+                sl.mask[4 * lane + 0] = cur.rec.x; sl.mask[4 * lane + 1] = cur.rec.y; sl.mask[4 * lane + 2] = cur.rec.z; sl.mask[4 * lane + 3] = cur.rec.w;
+                if (lane == 0) slot_n[k] = TS_RAW;
             }
             __syncwarp();
-            for (uint32_t base = 0; base < r.total; base += 32) {
-                const bool valid = base + lane < r.total;
-                const uint32_t tile = valid ? (buf[base + lane].x & 0xffffu) : 0u;
-                const unsigned m = warp_match<16>(tile, valid);
-                if (valid) buf[base + lane].y = m;
-            }
-            __syncwarp();
+            if (lane == 0) bin_mbar_arrive(&full[k]);   // release: the slot's contents are visible to the ranker
         }
-        bin_mbar_wait(&tbar[warp], phase);
-        for (uint32_t base = 0; base < r.total; base += 32) {
-            uint32_t tile = BIN_NONE, owner = 0;
-            unsigned m = 0;
-            if (staged) {
-                int olane = 0;
-                if (base + lane < r.total) {
-                    const uint2 v = buf[base + lane];
-                    tile = v.x & 0xffffu;
-                    olane = (int)(v.x >> 16);
-                    m = v.y;
+        return;
+    }
+
+    // ---- the ranker ----
+    for (int t = 0; t < nrows; t++) {
+        const int k = t % TS_SLOTS;
+        const uint32_t ph = (uint32_t)(t / TS_SLOTS) & 1u;
+        bin_mbar_wait(&full[k], ph);
+        const TileSlot& sl = slots[k];
+        const uint32_t n = slot_n[k];
+        if (n != TS_RAW) {
+            for (uint32_t base = 0; base < n; base += 32) {
+                const bool valid = base + lane < n;
+                uint32_t tile = 0, id = 0;
+                unsigned m = 0;
+                if (valid) {
+                    tile = sl.tile[base + lane];
+                    m = sl.mask[base + lane];
+                    id = sl.id[base + lane];
                 }
-                owner = __shfl_sync(FULL, r.id, olane);
-            } else {   // a row of screen-filling splats: generate inside the turn
+                const int leader = __ffs(m) - 1;
+                uint32_t old = 0;
+                if (valid && lane == leader) {
+                    old = cursor[tile];
+                    cursor[tile] = old + (uint32_t)__popc(m);
+                }
+                __syncwarp();
+                const uint32_t pos = __shfl_sync(FULL, old, leader & 31) + (uint32_t)__popc(m & lt);
+                if (valid && pos < capacity) point_list[pos] = id;
+            }
+        } else {
+            BinRowRaw raw;
+            raw.id = sl.id[lane];
+            raw.rec = make_uint4(sl.mask[4 * lane + 0], sl.mask[4 * lane + 1], sl.mask[4 * lane + 2], sl.mask[4 * lane + 3]);
+            BinRow r;
+            bin_row_decode(raw, lane, r);
+            for (uint32_t base = 0; base < r.total; base += 32) {
+                uint32_t owner;
                 int olane;
-                tile = bin_row_instance(r, base + lane, gx, owner, olane);
-                m = warp_match<16>(tile, tile != BIN_NONE);
+                const uint32_t tile = bin_row_instance(r, base + lane, gx, owner, olane);
+                const bool valid = tile != BIN_NONE;
+                const unsigned m = warp_match<16>(tile, valid);
+                const int leader = __ffs(m) - 1;
+                uint32_t old = 0;
+                if (valid && lane == leader) {
+                    old = cursor[tile];
+                    cursor[tile] = old + (uint32_t)__popc(m);
+                }
+                __syncwarp();
+                const uint32_t pos = __shfl_sync(FULL, old, leader & 31) + (uint32_t)__popc(m & lt);
+                if (valid && pos < capacity) point_list[pos] = owner;
             }
-            const int leader = __ffs(m) - 1;
-            uint32_t old = 0;
-            if (tile != BIN_NONE && lane == leader) {
-                old = cursor[tile];
-                cursor[tile] = old + (uint32_t)__popc(m);
-            }
-            __syncwarp();
-            const uint32_t pos = __shfl_sync(FULL, old, leader & 31) + (uint32_t)__popc(m & lt);
-            if (tile != BIN_NONE && pos < capacity) point_list[pos] = owner;
         }
         __syncwarp();
-        if (lane == 0) bin_mbar_arrive(&tbar[(warp + 1) % NW]);   // release: the next row's warp may go
+        if (lane == 0) bin_mbar_arrive(&empty[k]);
     }
 }
 
