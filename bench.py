@@ -816,9 +816,11 @@ def main():
     xdesc, xbytes = None, None
     if fused_exchange:
         mode, rows = rasterizer.exchange_info(world)
-        if mode == "sparse-p2p":
-            xdesc = (f"sparse over NVLink peer memory: each rank publishes bitmap + 64-byte rows of the Gaussians with a non-zero gradient "
-                     f"({rows} of {P} in rank 0's last view) and reads every peer's rows in its accumulate kernel; no NCCL call")
+        if mode.startswith("sparse-p2p"):
+            how = ("WRITES them into every peer's buffer from inside its pack kernel (posted stores over NVLink); after one barrier each rank "
+                   "accumulates from local memory") if mode.endswith("push") else "and reads every peer's rows in its accumulate kernel"
+            xdesc = (f"sparse over NVLink peer memory ({mode}): each rank packs bitmap + 64-byte rows of the Gaussians with a non-zero gradient "
+                     f"({rows} of {P} in rank 0's last view) {how}; no NCCL call")
             xbytes = (world - 1) * (rows * 64 + P // 4)
         else:
             xdesc = "dense (NCCL): all-reduce 44 B/Gaussian + all-gather dRGB 12 B/Gaussian/rank, SH gradient rebuilt locally"

@@ -11,7 +11,8 @@ CSRC = os.path.join(_HERE, "csrc")
 LIB_DIR = os.path.join(_HERE, "_lib")
 LIB_PATH = os.path.join(LIB_DIR, "liblgrast.so")
 SOURCES = ["lgrast.cu"]
-HEADERS = ["lgr_math.cuh", "lgr_blend.cuh", "lgr_raw.cuh", "lgr_sparse.cuh", "lgr_loss.cuh", "lgr_optim.cuh", "lgr_vq.cuh", os.path.join("..", "..", "include", "lgrast.h")]
+# every header under csrc/ (a header missing from this list once let an edited kernel run as its previous binary) + the C-ABI header
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + [os.path.join("..", "..", "include", "lgrast.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
