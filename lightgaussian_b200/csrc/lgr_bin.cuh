@@ -74,19 +74,24 @@ __device__ __forceinline__ void bin_mbar_arrive(uint64_t* bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bin_smem_u32(bar)) : "memory");
 }
+// SLEEP_NS > 0: back off between polls.  Measured (profiles/r02e): a warp polling a barrier -- try_wait returns within tens of
+// nanoseconds whatever suspend-time hint it is given -- takes issue slots and shared-memory bandwidth from the warps that work; with
+// seven waiting warps per block the one working warp ran 5-10x slower.  So only the warp on the serial path polls hot.
+template <int SLEEP_NS>
 __device__ __forceinline__ void bin_mbar_wait(uint64_t* bar, uint32_t parity)
 {
     uint32_t ok = 0;
     for (uint32_t spin = 0; !ok; ++spin) {
-        // suspend-time hint: let the hardware park the warp (up to ~1 ms per try) instead of returning at once -- measured: without the
-        // hint the loop polled ~60 times per hand-off and the polling warps took half of the kernel's issue slots
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(ok)
-                     : "r"(bin_smem_u32(bar)), "r"(parity), "r"(1000000u)
+                     : "r"(bin_smem_u32(bar)), "r"(parity)
                      : "memory");
-        if (!ok && spin > (1u << 16)) {   // a protocol bug becomes an error, not a hung GPU
-            printf("lgrast: tile scatter turn barrier timed out (block %d warp %d)\n", (int)blockIdx.x, (int)(threadIdx.x >> 5));
-            __trap();
+        if (!ok) {
+            if (SLEEP_NS > 0) __nanosleep(SLEEP_NS);
+            if (spin > (1u << 24)) {   // a protocol bug becomes an error, not a hung GPU
+                printf("lgrast: tile scatter ring barrier timed out (block %d warp %d)\n", (int)blockIdx.x, (int)(threadIdx.x >> 5));
+                __trap();
+            }
         }
     }
 }
@@ -500,7 +505,7 @@ __global__ void __launch_bounds__(TB_THREADS) tile_scatter_kernel(const uint32_t
             bin_row_decode(cur, lane, r);
             const int k = t % TS_SLOTS;
             const uint32_t ph = (uint32_t)(t / TS_SLOTS) & 1u;
-            bin_mbar_wait(&empty[k], ph ^ 1u);   // passes at once the first time round
+            bin_mbar_wait<400>(&empty[k], ph ^ 1u);   // passes at once the first time round; producers can afford to doze
             TileSlot& sl = slots[k];
             if (r.total <= (uint32_t)TS_SLOT) {
                 if (__all_sync(FULL, r.area <= 64u)) {
@@ -542,7 +547,7 @@ __global__ void __launch_bounds__(TB_THREADS) tile_scatter_kernel(const uint32_t
     for (int t = 0; t < nrows; t++) {
         const int k = t % TS_SLOTS;
         const uint32_t ph = (uint32_t)(t / TS_SLOTS) & 1u;
-        bin_mbar_wait(&full[k], ph);
+        bin_mbar_wait<0>(&full[k], ph);
         const TileSlot& sl = slots[k];
         const uint32_t n = slot_n[k];
         if (n != TS_RAW) {
