@@ -35,7 +35,7 @@ constexpr int BIN_V = 592;            // blocks of every count / scatter kernel 
 constexpr int DS_BITS = 11;
 constexpr int DS_BINS = 1 << DS_BITS;
 constexpr uint32_t BIN_NONE = 0xffffffffu;
-constexpr int TB_THREADS = 256;       // tile scatter block: 8 warps
+constexpr int TB_THREADS = 192;       // tile scatter block: 5 producer warps + 1 ranking warp
 constexpr int TC_THREADS = 256;       // tile count block: 8 warps
 constexpr int TB_BUF = 256;           // instances of one 32-Gaussian row that fit a ring slot of the tile scatter
 constexpr int SCAN_THREADS = 512;     // scan block: 16 warps share the rows of a 32-bin strip
@@ -94,6 +94,18 @@ __device__ __forceinline__ void bin_mbar_wait(uint64_t* bar, uint32_t parity)
             }
         }
     }
+}
+
+// the same with a run-time number of key bits (tile indices: ceil(log2(tiles)) bits)
+__device__ __forceinline__ unsigned warp_match_bits(uint32_t key, bool valid, int bits)
+{
+    unsigned m = __ballot_sync(FULL, valid);
+    for (int b = 0; b < bits; b++) {
+        const bool bit = (key >> b) & 1u;
+        const unsigned bal = __ballot_sync(FULL, bit);
+        m &= bit ? bal : ~bal;
+    }
+    return valid ? m : 0u;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -449,7 +461,7 @@ __global__ void __launch_bounds__(TC_THREADS) tile_count_kernel(const uint32_t* 
     if (lane == 0 && area) atomicAdd(reinterpret_cast<unsigned*>(header + HDR_RENDERED), area);
 }
 
-// ---- tile scatter: seven producer warps, one ranking warp, a ring of row slots between them ----
+// ---- tile scatter: producer warps, one ranking warp, a ring of row slots between them ----
 constexpr int TS_SLOTS = 8;                 // rows in flight between producers and the ranker
 constexpr int TS_SLOT = TB_BUF;             // instances a slot holds (one 32-Gaussian row; larger rows travel raw)
 constexpr int TS_PRODUCERS = TB_THREADS / 32 - 1;
@@ -495,6 +507,8 @@ __global__ void __launch_bounds__(TB_THREADS) tile_scatter_kernel(const uint32_t
     const int lo = blockIdx.x * per_block, hi = min(P, lo + per_block);
     const int nrows = (hi - lo + 31) / 32;
     const unsigned lt = (1u << lane) - 1u;
+    int tbits = 1;
+    while ((1 << tbits) < tiles_pad) tbits++;
 
     if (warp < TS_PRODUCERS) {
         BinRowRaw next = bin_row_fetch(sorted_ids, bin_rec, lo + warp * 32 + lane, hi);
@@ -505,7 +519,7 @@ __global__ void __launch_bounds__(TB_THREADS) tile_scatter_kernel(const uint32_t
             bin_row_decode(cur, lane, r);
             const int k = t % TS_SLOTS;
             const uint32_t ph = (uint32_t)(t / TS_SLOTS) & 1u;
-            bin_mbar_wait<400>(&empty[k], ph ^ 1u);   // passes at once the first time round; producers can afford to doze
+            bin_mbar_wait<2000>(&empty[k], ph ^ 1u);   // passes at once the first time round; producers can afford to doze
             TileSlot& sl = slots[k];
             if (r.total <= (uint32_t)TS_SLOT) {
                 if (__all_sync(FULL, r.area <= 64u)) {
@@ -528,7 +542,7 @@ __global__ void __launch_bounds__(TB_THREADS) tile_scatter_kernel(const uint32_t
                 for (uint32_t base = 0; base < r.total; base += 32) {
                     const bool valid = base + lane < r.total;
                     const uint32_t tile = valid ? (uint32_t)sl.tile[base + lane] : 0u;
-                    const unsigned m = warp_match<16>(tile, valid);
+                    const unsigned m = warp_match_bits(tile, valid, tbits);
                     if (valid) sl.mask[base + lane] = m;
                 }
                 if (lane == 0) slot_n[k] = r.total;
@@ -581,7 +595,7 @@ __global__ void __launch_bounds__(TB_THREADS) tile_scatter_kernel(const uint32_t
                 int olane;
                 const uint32_t tile = bin_row_instance(r, base + lane, gx, owner, olane);
                 const bool valid = tile != BIN_NONE;
-                const unsigned m = warp_match<16>(tile, valid);
+                const unsigned m = warp_match_bits(tile, valid, tbits);
                 const int leader = __ffs(m) - 1;
                 uint32_t old = 0;
                 if (valid && lane == leader) {
