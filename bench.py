@@ -49,8 +49,8 @@ def parse_args():
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--cams", type=int, default=16, help="distinct synthetic cameras cycled through")
     ap.add_argument("--blend-mode", type=int, default=0, help="DIAGNOSTIC: 0 = ring blend kernels (default), 1 = the round-1 blend kernels")
-    ap.add_argument("--bin-mode", type=int, default=0, help="DIAGNOSTIC: 0 = hand-written binning, estimated blob size (default), 1 = exact blob "
-                    "size (one stream sync), 2 = the round-1 library sorts")
+    ap.add_argument("--bin-mode", type=int, default=2, help="binning: 2 = library radix sorts + scan (default, fastest measured), 0 = hand-written "
+                    "kernels, blob sized from an estimate, no host sync, 1 = hand-written kernels, exact blob size (one stream sync)")
     ap.add_argument("--kback-mode", type=int, default=0, help="DIAGNOSTIC: fused K7+K8 of the raw backward: 0 = rows cleared inside the blend "
                     "backward + compacted list (default), 1 = dense kernel, 2 = separate zero-fill kernel + compacted list")
     ap.add_argument("--no-cpu-baseline", action="store_true")

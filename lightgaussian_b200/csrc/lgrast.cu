@@ -44,11 +44,13 @@ constexpr int ACC_STRIDE = 12;  // floats per Gaussian in the backward accumulat
 
 thread_local std::string g_last_error;
 int g_blend_mode = 0;   // 0 = ring kernels (lgr_blend.cuh), 1 = round-1 kernels (kept for A/B measurements and as a cross-check in the tests)
-// binning (lgr_bin.cuh): 0 = hand-written kernels, binning blob sized from a running estimate, no GPU idle on the host (default);
-// 1 = hand-written kernels, blob sized exactly after a stream synchronisation; 2 = round-1 path (library radix sorts + scan, host sync)
-int g_bin_mode = 0;
-int g_kback_mode = 0;   // single-GPU K7+K8: 0 = rows cleared inside the blend backward + compacted list (lgr_sparse.cuh), 1 = dense kernel, 2 = separate zero-fill kernel + compacted list (A/B)
+// binning: 2 = library radix sorts + scan with one host synchronisation for the instance count (default: the fastest path measured,
+// 0.50 ms per view at 3M / 1080p); 0 = hand-written kernels (lgr_bin.cuh), binning blob sized from a running estimate, no GPU idle on the
+// host (0.76 ms: correct and library-free, but its serial tile-ranking warp is slower than two library radix passes -- DESIGN.md section 9);
+// 1 = hand-written kernels, blob sized exactly after a stream synchronisation
+int g_bin_mode = 2;
 std::atomic<size_t> g_bin_hint{0};   // running estimate of the listed instances per view (mode 0)
+int g_kback_mode = 0;   // single-GPU K7+K8: 0 = rows cleared inside the blend backward + compacted list (lgr_sparse.cuh), 1 = dense kernel, 2 = separate zero-fill kernel + compacted list (A/B)
 std::atomic<uint64_t> g_launches{0};
 
 // ---- optional per-stage device timing (CUDA events on the launch stream), used by bench.py's roofline ----
@@ -1432,7 +1434,7 @@ int lgr_set_blend_mode(int mode)
 int lgr_set_binning_mode(int mode)
 {
     if (mode < 0 || mode > 2) {
-        g_last_error = "lgr_set_binning_mode: 0 = hand-written kernels, estimated blob size (default), 1 = hand-written kernels, exact blob size, 2 = library sorts";
+        g_last_error = "lgr_set_binning_mode: 0 = hand-written kernels, estimated blob size, 1 = hand-written kernels, exact blob size, 2 = library sorts (default)";
         return LGR_ERR_INVALID_ARG;
     }
     g_bin_mode = mode;

@@ -52,7 +52,7 @@ def _empty():
 
 
 def run_ours(view: View, act: dict, count=False, dL_dpix=None, colors_precomp=None, cov3D_precomp=None, debug=False, tile_cull=True,
-             blend_mode=0, bin_mode=0):
+             blend_mode=0, bin_mode=None):
     """tile_cull=False makes the per-tile lists identical to the reference's (needed to compare point_list / ranges /
     n_contrib); the product default (True) lists only instances that can contribute."""
     import torch
@@ -61,13 +61,13 @@ def run_ours(view: View, act: dict, count=False, dL_dpix=None, colors_precomp=No
     dev = "cuda"
     capi.set_tile_culling(tile_cull)
     capi.set_blend_mode(blend_mode)      # 0 = ring kernels (the product default), 1 = the round-1 kernels
-    capi.set_binning_mode(bin_mode)      # 0 = hand-written binning, estimated blob (default); 1 = exact blob; 2 = round-1 library sorts
+    capi.set_binning_mode(capi.DEFAULT_BINNING_MODE if bin_mode is None else bin_mode)   # 2 = library sorts (default); 0 / 1 = hand-written
     try:
         return _run_ours(view, act, count, dL_dpix, colors_precomp, cov3D_precomp, debug)
     finally:
         capi.set_tile_culling(True)
         capi.set_blend_mode(0)
-        capi.set_binning_mode(0)
+        capi.set_binning_mode(capi.DEFAULT_BINNING_MODE)
 
 
 def _run_ours(view, act, count, dL_dpix, colors_precomp, cov3D_precomp, debug):
