@@ -753,6 +753,14 @@ def main():
                         rows[kname] = {"ms_per_launch": ms1, "alg_bytes": alg_rows[kname], "gbs": alg_rows[kname] / (ms1 * 1e-3) / 1e9,
                                        "frac_of_hbm_peak": alg_rows[kname] / (ms1 * 1e-3) / 1e9 / peak_rows}
                 iteration_pass["kernels"] = rows
+                # every native stage of one iteration (ms per iteration, this rank): where a view-parallel iteration spends its time
+                iteration_pass["stages_ms_per_iteration"] = {k: ms_tot / 5 for k, (ms_tot, nl) in prof_rows.items() if nl}
+                t_h0 = time.perf_counter()
+                for s_ in range(5):
+                    fn(100 + s_)
+                t_h1 = time.perf_counter()           # host time to ENQUEUE an iteration (no synchronisation inside)
+                torch.cuda.synchronize()
+                iteration_pass["host_enqueue_ms_per_iteration"] = (t_h1 - t_h0) * 1e3 / 5
             del opt
         zero_grads()
 
