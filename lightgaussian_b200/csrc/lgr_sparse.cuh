@@ -92,10 +92,14 @@ __global__ void __launch_bounds__(256) sparse_publish_kernel(SparsePush push, in
     }
 }
 
-__global__ void __launch_bounds__(256) preprocess_backward_sparse_kernel(RawBackArgs a, const int* __restrict__ idx, const uint32_t* __restrict__ hdr,
-                                                                         SparsePush push, size_t rows_off)
+constexpr int SPK_THREADS = 128;
+constexpr int SPK_ROW = 49;   // floats per staged SH row (48 + 1: conflict-free at one row per lane)
+
+__global__ void __launch_bounds__(SPK_THREADS) preprocess_backward_sparse_kernel(RawBackArgs a, const int* __restrict__ idx, const uint32_t* __restrict__ hdr,
+                                                                                 SparsePush push, size_t rows_off)
 {
     __shared__ float s_cam[36];
+    __shared__ float s_sh[SPK_THREADS / 32][32 * SPK_ROW];
     if (threadIdx.x < 16) s_cam[threadIdx.x] = a.view[threadIdx.x];
     else if (threadIdx.x < 32) s_cam[threadIdx.x] = a.proj[threadIdx.x - 16];
     else if (threadIdx.x < 35) s_cam[threadIdx.x] = a.campos[threadIdx.x - 32];
@@ -103,10 +107,44 @@ __global__ void __launch_bounds__(256) preprocess_backward_sparse_kernel(RawBack
     const float* view = s_cam;
     const float* proj = s_cam + 16;
     const float* cam = s_cam + 32;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int count = (int)hdr[3];
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (int)hdr[3]) return;
-    const int i = idx[t];
-    const size_t si = (size_t)i;
+    if (t - lane >= count) return;   // whole warp past the list
+    const bool valid = t < count;
+    const int i = valid ? idx[t] : -1;
+    const size_t si = (size_t)(valid ? i : 0);
+    // the SH coefficients feed only the view-direction term of dL/dmean3D (degree >= 1): the warp's 32 scattered rows are staged through
+    // shared memory with row-contiguous loads (3 instructions per row, eight rows in flight) instead of 48 strided loads per lane
+    float* rows = s_sh[warp];
+    const int nrest_act = 3 * ((a.D + 1) * (a.D + 1) - 1);
+    if (a.D > 0) {
+#pragma unroll 1
+        for (int r0 = 0; r0 < 32; r0 += 8) {
+            float v0[8], v1[8], v2[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int ir = __shfl_sync(FULL, i, r0 + u);
+                v0[u] = v1[u] = v2[u] = 0.f;
+                if (ir >= 0) {
+                    const float* src = a.rest + (size_t)ir * a.rest_stride;
+                    if (lane < 3) v0[u] = __ldg(a.dc + (size_t)ir * 3 + lane);
+                    if (lane < nrest_act) v1[u] = __ldg(src + lane);
+                    if (lane + 32 < nrest_act) v2[u] = __ldg(src + 32 + lane);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                float* dst = rows + (r0 + u) * SPK_ROW;
+                if (lane < 3) dst[lane] = v0[u];
+                if (lane < nrest_act) dst[3 + lane] = v1[u];
+                if (lane + 32 < nrest_act) dst[3 + 32 + lane] = v2[u];
+            }
+        }
+        __syncwarp();
+    }
+    if (!valid) return;
+    const float* mine = rows + lane * SPK_ROW;
 
     float dmean[3] = {0.f, 0.f, 0.f}, dscale[3], dq[4], dRGB[3];
     const float4 co = a.conic_opacity[si];
@@ -132,11 +170,8 @@ __global__ void __launch_bounds__(256) preprocess_backward_sparse_kernel(RawBack
     dq[2] = (dqn[2] - q.z * qg) * inv; dq[3] = (dqn[3] - q.w * qg) * inv;
     const float o = co.w;
     const float dop = (g2.dop * (1.0f - o)) * o;
-    if (a.D > 0) {  // view-direction term of dL/dmean3D; the SH gradient itself is rebuilt from dRGB by the accumulate kernel
-        const float* rr = a.rest + si * a.rest_stride;
-        const float* dd = a.dc + si * 3;
-        lgr::sh_backward(a.D, [&](int k) { return k < 3 ? dd[k] : rr[k - 3]; }, [](int, int, float) {}, x, y, z, cam, dRGB, dmean);
-    }
+    if (a.D > 0)   // view-direction term of dL/dmean3D; the SH gradient itself is rebuilt from dRGB by the accumulate kernel
+        lgr::sh_backward(a.D, [&](int k) { return mine[k]; }, [](int, int, float) {}, x, y, z, cam, dRGB, dmean);
     const float4 v0 = make_float4(dRGB[0], dRGB[1], dRGB[2], dmean[0]);
     const float4 v1 = make_float4(dmean[1], dmean[2], dscale[0], dscale[1]);
     const float4 v2 = make_float4(dscale[2], dq[0], dq[1], dq[2]);

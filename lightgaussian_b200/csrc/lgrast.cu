@@ -1849,7 +1849,7 @@ int lgr_backward_raw_sparse_pack_push(const lgr_view* v, int P, int M, const lgr
         LGR_CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, popc, xb + L.prefix, w32, stream));
         sparse_index_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, xb + L.bitmap, xb + L.prefix, idx, xb + L.hdr, v->campos);
         if (world > 1) sparse_publish_kernel<<<148, 256, 0, stream>>>(push, self, L.rows);
-        preprocess_backward_sparse_kernel<<<(P + 255) / 256, 256, 0, stream>>>(a, idx, xb + L.hdr, push, L.rows);
+        preprocess_backward_sparse_kernel<<<(P + SPK_THREADS - 1) / SPK_THREADS, SPK_THREADS, 0, stream>>>(a, idx, xb + L.hdr, push, L.rows);
     }
     LGR_LAUNCH_CHECK("preprocess_backward_sparse_kernel", debug, stream);
     return LGR_OK;
