@@ -251,6 +251,11 @@ int lgr_compact_rows(int rows_out, const int32_t* src_row, int n_tensors, const 
  * lgr_vq_pack_indices / lgr_vq_unpack_indices: `bits` bits per index, most significant first, bytes filled from the high bit
  *   (dec2bin + np.packbits, vectree.py:120-125; np.unpackbits + bin2dec, vectree/utils.py:33-39); out has (n*bits+7)/8 bytes. */
 size_t lgr_vq_workspace_bytes(int64_t n);
+/* lgr_vq_assign for d <= 32 and n*K >= 2^20 runs the scores on the tensor cores (csrc/lgr_vq_tc.cuh: bf16 hi/lo split operands, tcgen05.mma,
+ * accumulators in TMEM) and re-scores in exact FP32 only the rows whose two best codes are closer than the split's error bound; indices are
+ * the same as the FP32 kernel's.  lgr_set_vq_mode(1) forces the FP32 kernel (A/B measurements).  The tensor-core path keeps a grow-only
+ * device scratch (operand tiles) inside the library. */
+int lgr_set_vq_mode(int mode);
 int lgr_vq_assign(int n, int d, int K, const float* x, const float* embed, const float* weight, const float* weight_sum, int32_t* idx,
                   float* cluster_batch, float* embed_sum, void* workspace, void* cuda_stream);
 int lgr_vq_ema_update(int K, int d, double decay, double eps, float* cluster_size, float* embed, const float* cluster_batch,

@@ -263,6 +263,11 @@ def binning_overflows() -> int:
     return int(load().lgr_binning_overflows())
 
 
+def set_vq_mode(mode: int) -> None:
+    """VecTree nearest-code search: 0 = tensor-core coarse pass + exact FP32 rescore (default), 1 = FP32 kernel only"""
+    check(load().lgr_set_vq_mode(int(mode)), "lgr_set_vq_mode")
+
+
 def set_kback_mode(mode: int) -> None:
     """fused K7+K8 of the raw backward: 0 = zero-fill + compacted list (default), 1 = dense kernel (A/B measurements)"""
     check(load().lgr_set_kback_mode(int(mode)), "lgr_set_kback_mode")

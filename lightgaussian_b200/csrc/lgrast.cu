@@ -50,6 +50,7 @@ int g_blend_mode = 0;   // 0 = ring kernels (lgr_blend.cuh), 1 = round-1 kernels
 // 1 = hand-written kernels, blob sized exactly after a stream synchronisation
 int g_bin_mode = 2;
 std::atomic<size_t> g_bin_hint{0};   // running estimate of the listed instances per view (mode 0)
+int g_vq_mode = 0;      // VecTree nearest-code search: 0 = tensor-core coarse pass + exact FP32 rescore (d <= 32), 1 = FP32 FFMA kernel only
 int g_kback_mode = 0;   // single-GPU K7+K8: 0 = rows cleared inside the blend backward + compacted list (lgr_sparse.cuh), 1 = dense kernel, 2 = separate zero-fill kernel + compacted list (A/B)
 std::atomic<uint64_t> g_launches{0};
 
@@ -1064,6 +1065,7 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(PreBackArgs a)
 #include "lgr_loss.cuh"
 #include "lgr_optim.cuh"
 #include "lgr_vq.cuh"
+#include "lgr_vq_tc.cuh"
 namespace {
 
 // ------------------------------------------------------------------------------------------------
@@ -1448,6 +1450,16 @@ int lgr_set_kback_mode(int mode)
         return LGR_ERR_INVALID_ARG;
     }
     g_kback_mode = mode;
+    return LGR_OK;
+}
+
+int lgr_set_vq_mode(int mode)
+{
+    if (mode != 0 && mode != 1) {
+        g_last_error = "lgr_set_vq_mode: 0 = tcgen05 coarse pass + exact FP32 rescore (default), 1 = FP32 kernel only";
+        return LGR_ERR_INVALID_ARG;
+    }
+    g_vq_mode = mode;
     return LGR_OK;
 }
 
@@ -2174,7 +2186,52 @@ int lgr_vq_assign(int n, int d, int K, const float* x, const float* embed, const
     if (embed_sum) LGR_CUDA_TRY(cudaMemsetAsync(embed_sum, 0, sizeof(float) * (size_t)K * d, stream));
     if (n == 0) return LGR_OK;
     unsigned long long* best = static_cast<unsigned long long*>(workspace);
-    {
+    if (g_vq_mode == 0 && d <= VT_DP && (long long)n * K >= (1ll << 20)) {
+        // coarse pass on the tensor cores (tcgen05, lgr_vq_tc.cuh) + exact FP32 rescore of the undecided rows
+        const int n_pad = (n + VT_M - 1) / VT_M * VT_M, K_pad = (K + VT_N - 1) / VT_N * VT_N;
+        const size_t oA = 0, oB = oA + vt_align((size_t)(n_pad / VT_M) * VT_A_BYTES), oN = oB + vt_align((size_t)(K_pad / VT_N) * VT_B_BYTES),
+                     oX = oN + vt_align((size_t)K_pad * 4), oC = oX + vt_align((size_t)n_pad * 4), oL = oC + 1024, total = oL + vt_align((size_t)n * 4);
+        int dev = 0;
+        LGR_CUDA_TRY(cudaGetDevice(&dev));
+        static VtScratch scratch[16];
+        static std::mutex scratch_mutex;
+        char* sp = nullptr;
+        {
+            std::lock_guard<std::mutex> l(scratch_mutex);
+            VtScratch& sc = scratch[dev & 15];
+            if (sc.bytes < total) {   // grow-only; cudaMalloc synchronises, but only when a larger problem shows up
+                if (sc.p) LGR_CUDA_TRY(cudaFree(sc.p));
+                sc.p = nullptr; sc.bytes = 0;
+                LGR_CUDA_TRY(cudaMalloc(&sc.p, total + total / 4));
+                sc.bytes = total + total / 4;
+            }
+            sp = static_cast<char*>(sc.p);
+        }
+        unsigned char* tA = reinterpret_cast<unsigned char*>(sp + oA);
+        unsigned char* tB = reinterpret_cast<unsigned char*>(sp + oB);
+        float* norms = reinterpret_cast<float*>(sp + oN);
+        float* xnorm = reinterpret_cast<float*>(sp + oX);
+        unsigned* emax = reinterpret_cast<unsigned*>(sp + oC);
+        int* n_und = reinterpret_cast<int*>(sp + oC + 4);
+        int* und = reinterpret_cast<int*>(sp + oL);
+        {
+            ProfScope ps(ST_VQ_ASSIGN, stream);
+            LGR_CUDA_TRY(cudaMemsetAsync(sp + oC, 0, 8, stream));
+            vt_prep_x_kernel<<<(n_pad + 255) / 256, 256, 0, stream>>>(n, n_pad, d, x, tA, xnorm);
+            vt_prep_e_kernel<<<(K_pad + 255) / 256, 256, 0, stream>>>(K, K_pad, d, embed, tB, norms, emax);
+            LGR_CUDA_TRY(cudaFuncSetAttribute(vt_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VtSmem)));
+            vt_assign_kernel<<<n_pad / VT_M, VT_THREADS, sizeof(VtSmem), stream>>>(n, K_pad, tA, tB, norms, xnorm, emax, best, und, n_und);
+            constexpr int RXR = 4;
+            const int row_tiles = (n + RXR * VQ_THREADS - 1) / (RXR * VQ_THREADS);
+            const int code_tiles = (K + VQ_TC - 1) / VQ_TC;
+            int splits = std::max(1, std::min(code_tiles, 64));
+            const int codes_per_split = (code_tiles + splits - 1) / splits * VQ_TC;
+            splits = (K + codes_per_split - 1) / codes_per_split;
+            vq_assign_rows_kernel<VT_DP, RXR><<<dim3(row_tiles, splits), VQ_THREADS, 0, stream>>>(und, n_und, d, K, x, embed, codes_per_split, best);
+            g_launches.fetch_add(3, std::memory_order_relaxed);
+        }
+        LGR_LAUNCH_CHECK("vt_assign_kernel", false, stream);
+    } else {
         ProfScope ps(ST_VQ_ASSIGN, stream);
         vq_init_best_kernel<<<(n + 255) / 256, 256, 0, stream>>>(n, best);
         if (d <= 8) vq_launch_assign<8>(n, d, K, x, embed, best, stream);
@@ -2183,8 +2240,8 @@ int lgr_vq_assign(int n, int d, int K, const float* x, const float* embed, const
         else if (d <= 32) vq_launch_assign<32>(n, d, K, x, embed, best, stream);
         else if (d <= 48) vq_launch_assign<48>(n, d, K, x, embed, best, stream);
         else vq_launch_assign<64>(n, d, K, x, embed, best, stream);
+        LGR_LAUNCH_CHECK("vq_assign_kernel", false, stream);
     }
-    LGR_LAUNCH_CHECK("vq_assign_kernel", false, stream);
     const long long total = (long long)n * (d + 1);
     vq_accumulate_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(n, d, best, x, weight, (float)n, weight_sum, idx, cluster_batch,
                                                                                  embed_sum);

@@ -172,3 +172,32 @@ def test_full_size_iteration_against_the_torch_formulation():
 def test_cpu_tensors_are_refused():
     with pytest.raises(RuntimeError):
         vt.vq_assign(torch.zeros(4, 27), torch.zeros(8, 27))
+
+
+def test_tensor_core_search_equals_the_fp32_kernel_at_full_size():
+    """80 000 x 8192 x 27 (vectree/vq.py's chunk): the tcgen05 coarse pass + exact rescore of the undecided rows must return the FP32
+    kernel's indices -- both kernels break exact ties towards the smaller index; rows whose two best codes differ by less than the fp32
+    rounding of the expansion may legitimately differ and are checked in float64"""
+    from lightgaussian_b200 import capi
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn(80000, 27, device="cuda", generator=g) * 0.5
+    e = torch.randn(8192, 27, device="cuda", generator=g) * 0.7
+    capi.set_vq_mode(1)
+    try:
+        ref = vt.vq_assign(x, e).cpu().numpy()
+    finally:
+        capi.set_vq_mode(0)
+    got = vt.vq_assign(x, e).cpu().numpy()
+    assert _ties_only(x.cpu().numpy(), e.cpu().numpy(), got, ref)
+    assert (got != ref).mean() < 1e-4
+    # clustered data (what k-means converges to): many samples sit next to their code, runner-ups are far
+    centers = torch.randn(8192, 27, device="cuda", generator=g)
+    xc = centers[torch.randint(0, 8192, (80000,), device="cuda", generator=g)] + 0.05 * torch.randn(80000, 27, device="cuda", generator=g)
+    capi.set_vq_mode(1)
+    try:
+        ref = vt.vq_assign(xc, centers).cpu().numpy()
+    finally:
+        capi.set_vq_mode(0)
+    got = vt.vq_assign(xc, centers).cpu().numpy()
+    assert _ties_only(xc.cpu().numpy(), centers.cpu().numpy(), got, ref)
+    assert (got != ref).mean() < 1e-4
