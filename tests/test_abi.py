@@ -87,3 +87,23 @@ def test_product_never_imports_the_oracle():
             for f in files:
                 if f.endswith(".py"):
                     assert "oracle" not in open(os.path.join(dirpath, f)).read()
+
+
+def test_build_hash_covers_every_kernel_header():
+    """a header missing from the staleness hash once let an edited kernel run as its previous binary"""
+    from lightgaussian_b200 import build
+    on_disk = {f for f in os.listdir(build.CSRC) if f.endswith((".cuh", ".h"))}
+    assert on_disk and on_disk <= set(build.HEADERS), on_disk - set(build.HEADERS)
+    for inc in re.findall(r'#include "([^"]+)"', open(os.path.join(build.CSRC, "lgrast.cu")).read()):
+        if not inc.startswith(".."):
+            assert inc in build.HEADERS, inc
+
+
+def test_bench_cli_parses():
+    """bench.py is the driver's contract: a syntax error or a broken option must show up on the CPU box"""
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--help"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    for opt in ("--gpus", "--steps", "--warmup", "--impl", "--mode", "--bin-mode", "--kback-mode"):
+        assert opt in r.stdout
